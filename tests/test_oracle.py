@@ -1,0 +1,251 @@
+"""Pins the CPU oracle (oracle/p3_oracle.c) against the reference's own known answers.
+
+Everything here runs on CPU.  The oracle is what the GPU parity tests compare against, so it is
+checked first against: field KATs, the two-adic generator tables, NaiveDft, Poseidon2 KATs, FIPS-202
+(Keccak), structural Merkle identities from the reference's tests, and the committed proof fixture.
+"""
+import hashlib
+import json
+import pathlib
+
+import numpy as np
+import pytest
+
+from oracle import p3_oracle as O
+import fixture_replay as FR
+
+GOLD = pathlib.Path(__file__).resolve().parent / "golden"
+BB, KB = O.BABY_BEAR, O.KOALA_BEAR
+
+
+def test_field_mul_kat():
+    # baby-bear/src/baby_bear.rs:178-181, koala-bear/src/koala_bear.rs:182-185
+    for f, exp in ((BB, 0x1B5C8046), (KB, 0x54B46B81)):
+        m1, m2 = O.to_monty(f, 0x34167C58), O.to_monty(f, 0x61F3207B)
+        assert O.from_monty(f, O.mul(f, m1, m2)) == exp
+
+
+def test_monty_constants():
+    # SURVEY Appendix A (derived from baby_bear.rs:17-20, koala_bear.rs:20-23)
+    assert O.to_monty(BB, 1) == 0x0FFFFFFE and O.to_monty(KB, 1) == 0x01FFFFFE
+    for f in (BB, KB):
+        p = O.prime(f)
+        for a, b in ((0, 0), (1, p - 1), (p - 1, p - 1), (12345, 678910)):
+            am, bm = O.to_monty(f, a), O.to_monty(f, b)
+            assert O.from_monty(f, O.add(f, am, bm)) == (a + b) % p
+            assert O.from_monty(f, O.sub(f, am, bm)) == (a - b) % p
+            assert O.from_monty(f, O.mul(f, am, bm)) == a * b % p
+            assert O.from_monty(f, O.halve(f, am)) == a * pow(2, p - 2, p) % p
+
+
+def test_two_adic_generators():
+    # baby_bear.rs:48-53,150-158 ; koala_bear.rs:73-78,163-171
+    gens = json.loads((GOLD / "two_adic_generators.json").read_text())
+    for f, name in ((BB, "baby_bear"), (KB, "koala_bear")):
+        for bits, g in enumerate(gens[name]):
+            assert O.from_monty(f, O.two_adic_generator(f, bits)) == g
+
+
+@pytest.mark.parametrize("f", [BB, KB])
+@pytest.mark.parametrize("log_h,w", [(0, 3), (1, 2), (3, 5), (6, 3), (8, 1)])
+def test_dft_matches_naive(f, log_h, w):
+    # dft/tests/testing.rs:298-378: every backend must agree with NaiveDft
+    m = O.random_matrix(f, 1 << log_h, w, seed=log_h * 10 + w)
+    assert np.array_equal(O.dft_batch(f, m), O.naive_dft(f, m))
+
+
+def test_naive_dft_literal():
+    # dft/src/naive.rs:46-85 style: DFT of a delta is all-ones; DFT of ones is h*delta
+    f = BB
+    one = O.to_monty(f, 1)
+    m = np.zeros((8, 1), dtype=np.uint32); m[0, 0] = one
+    assert (O.naive_dft(f, m) == one).all()
+    m[:] = one
+    out = O.naive_dft(f, m)
+    assert out[0, 0] == O.to_monty(f, 8) and (out[1:] == 0).all()
+
+
+@pytest.mark.parametrize("f", [BB, KB])
+def test_dft_roundtrips_and_cosets(f):
+    # dft/tests/testing.rs:380-452 (round trips), traits.rs:84-155 (coset definitions)
+    m = O.random_matrix(f, 64, 7, seed=3)
+    assert np.array_equal(O.idft_batch(f, O.dft_batch(f, m)), m)
+    s = O.to_monty(f, 0x1234567)
+    assert np.array_equal(O.coset_idft_batch(f, O.coset_dft_batch(f, m, s), s), m)
+    # coset dft by definition: evaluate the polynomial at s*w^i
+    p = O.prime(f); co = O.from_monty_arr(f, m[:, 0]).astype(object)
+    w = O.from_monty(f, O.two_adic_generator(f, 6)); sc = O.from_monty(f, s)
+    ev = O.from_monty_arr(f, O.coset_dft_batch(f, m, s)[:, 0])
+    for i in (0, 1, 17, 63):
+        x = sc * pow(w, i, p) % p
+        assert int(ev[i]) == sum(int(c) * pow(x, j, p) for j, c in enumerate(co)) % p
+
+
+@pytest.mark.parametrize("f", [BB, KB])
+@pytest.mark.parametrize("added_bits", [0, 1, 2, 3])
+def test_coset_lde_layout(f, added_bits):
+    # traits.rs:227-259 (definition) + radix_2_dit_parallel.rs:181-246 / two_adic_pcs.rs:313-318 (bit-reversed rows)
+    h, w = 16, 3
+    m = O.random_matrix(f, h, w, seed=7)
+    shift = O.generator(f)
+    nat = O.coset_lde_batch(f, m, added_bits, shift, bitrev_out=False)
+    brv = O.coset_lde_batch(f, m, added_bits, shift, bitrev_out=True)
+    assert np.array_equal(O.reverse_matrix_index_bits(nat), brv)
+    # definition: idft, zero-pad, coset dft
+    co = O.idft_batch(f, m)
+    pad = np.zeros((h << added_bits, w), dtype=np.uint32); pad[:h] = co
+    assert np.array_equal(O.coset_dft_batch(f, pad, shift), nat)
+    # first h memory rows of the bit-reversed LDE are the evaluations on shift*H (bit-reversed)
+    assert np.array_equal(brv[:h], O.reverse_matrix_index_bits(O.coset_dft_batch(f, co, shift)))
+
+
+def test_poseidon2_kats():
+    # koala-bear/src/poseidon2.rs:614-653, baby-bear/src/poseidon2.rs:599-639
+    kats = json.loads((GOLD / "poseidon2_kat.json").read_text())
+    for f, name in ((BB, "baby_bear"), (KB, "koala_bear")):
+        for w in (16, 24):
+            k = kats[f"{name}_{w}"]
+            out = O.poseidon2_permute(O.default_perm(f, w), O.to_monty_arr(f, k["input"]))
+            assert O.from_monty_arr(f, out).tolist() == k["expected"]
+
+
+def test_poseidon2_diag_values():
+    # koala-bear/src/poseidon2.rs:410-428: V16 = [-2,1,2,1/2,3,4,-1/2,-3,-4,2^-8,1/8,2^-24,-2^-8,-1/8,-1/16,-2^-24]
+    p = O.prime(KB); i2 = lambda k: pow(pow(2, k, p), p - 2, p)
+    exp = [p - 2, 1, 2, i2(1), 3, 4, p - i2(1), p - 3, p - 4, i2(8), i2(3), i2(24), p - i2(8), p - i2(3), p - i2(4), p - i2(24)]
+    assert O.from_monty_arr(KB, O.poseidon2_diag(KB, 16)).tolist() == exp
+
+
+def _sha3_256_via_oracle(msg: bytes) -> bytes:
+    rate = 136
+    padded = bytearray(msg) + b"\x06" + b"\x00" * ((-len(msg) - 2) % rate) + b"\x80" if (len(msg) + 1) % rate else bytearray(msg) + b"\x86"
+    st = np.zeros(25, dtype=np.uint64)
+    for off in range(0, len(padded), rate):
+        blk = np.frombuffer(bytes(padded[off:off + rate]), dtype="<u8")
+        st[:17] ^= blk
+        st = O.keccak_f(st)
+    return st[:4].astype("<u8").tobytes()
+
+
+def test_keccak_f_fips202():
+    # tiny-keccak is not vendored; pin Keccak-f[1600] with FIPS-202 SHA3-256 (hashlib)
+    for msg in (b"", b"abc", bytes(range(200)), b"x" * 135, b"y" * 136):
+        assert _sha3_256_via_oracle(msg) == hashlib.sha3_256(msg).digest()
+
+
+def test_keccak_leaf_packing_and_compress():
+    # field/src/integers.rs:494-509 (pair packing), sponge.rs:182-216 (overwrite, no padding), compression.rs:60-70
+    hs = O.keccak_hasher()
+    row = np.arange(1, 38, dtype=np.uint32)                       # odd width 37 -> 19 words -> 2 permutations
+    words = [int(row[2 * i]) | (int(row[2 * i + 1]) << 32) for i in range(18)] + [int(row[36])]
+    st = np.zeros(25, dtype=np.uint64)
+    st[:17] = words[:17]; st = O.keccak_f(st)
+    st[:2] = words[17:]; st = O.keccak_f(st)
+    assert O.hash_row(hs, row).view(np.uint64).tolist() == st[:4].tolist()
+    l, r = O.hash_row(hs, row), O.hash_row(hs, row[:5])
+    st = np.zeros(25, dtype=np.uint64); st[:4] = l.view(np.uint64); st[4:8] = r.view(np.uint64)
+    assert O.compress(hs, l, r).view(np.uint64).tolist() == O.keccak_f(st)[:4].tolist()
+
+
+def _p2_hasher(f=KB, wl=16):
+    return O.poseidon2_hasher(O.default_perm(f, wl), O.default_perm(f, 16))
+
+
+def test_sponge_semantics():
+    # symmetric/src/sponge.rs:182-216: overwrite mode, partial last block keeps previous outputs, no padding
+    hs = _p2_hasher()
+    pm = O.default_perm(KB, 16)
+    row = O.random_matrix(KB, 1, 11, seed=5)[0]
+    st = np.zeros(16, dtype=np.uint32)
+    st[:8] = row[:8]; st = O.poseidon2_permute(pm, st)
+    st[:3] = row[8:]; st = O.poseidon2_permute(pm, st)
+    assert np.array_equal(O.hash_row(hs, row), st[:8])
+    # exact multiple of the rate: no extra permutation
+    st = np.zeros(16, dtype=np.uint32); st[:8] = row[:8]
+    assert np.array_equal(O.hash_row(hs, row[:8]), O.poseidon2_permute(pm, st)[:8])
+    # empty input: zero digest
+    assert (O.hash_row(hs, row[:0]) == 0).all()
+
+
+def test_merkle_structure_single_matrix():
+    # merkle-tree/src/mmcs/batch.rs:333-364: root == compress(compress(h,h), compress(h,h))
+    hs = _p2_hasher()
+    m = O.random_matrix(KB, 4, 9, seed=2)
+    layers = O.merkle_tree(hs, [m])
+    h = [O.hash_row(hs, m[i]) for i in range(4)]
+    root = O.compress(hs, O.compress(hs, h[0], h[1]), O.compress(hs, h[2], h[3]))
+    assert [len(l) for l in layers] == [4, 2, 1]
+    assert np.array_equal(layers[-1][0], root)
+    assert np.array_equal(O.merkle_cap(layers, 1), layers[1])
+    assert np.array_equal(O.merkle_cap(layers, 5), layers[0])       # clamp (mmcs/batch.rs:56-62)
+
+
+def test_merkle_mixed_heights_and_padding():
+    # merkle_tree.rs:348-460 (inject), :652-711 (zero-digest padding); two tallest matrices share a leaf hash
+    hs = _p2_hasher()
+    a, b = O.random_matrix(KB, 8, 3, seed=1), O.random_matrix(KB, 8, 2, seed=2)
+    c = O.random_matrix(KB, 4, 5, seed=3)
+    layers = O.merkle_tree(hs, [c, a, b])                            # input order: c first, but a,b are tallest
+    leaf = [O.hash_row(hs, np.concatenate([a[i], b[i]])) for i in range(8)]
+    l1 = [O.compress(hs, O.compress(hs, leaf[2 * i], leaf[2 * i + 1]), O.hash_row(hs, c[i])) for i in range(4)]
+    l2 = [O.compress(hs, l1[0], l1[1]), O.compress(hs, l1[2], l1[3])]
+    assert np.array_equal(layers[1], np.array(l1)) and np.array_equal(layers[2], np.array(l2))
+    # non power of two height 5 -> padded 6 -> 3 -> padded 4 -> 2 -> 1
+    m = O.random_matrix(KB, 5, 4, seed=4)
+    layers = O.merkle_tree(hs, [m])
+    assert [len(l) for l in layers] == [6, 4, 2, 1]
+    z = np.zeros(8, dtype=np.uint32)
+    assert (layers[0][5] == 0).all()
+    assert np.array_equal(layers[1][2], O.compress(hs, O.hash_row(hs, m[4]), z))
+    assert (layers[1][3] == 0).all()
+    with pytest.raises(ValueError):
+        O.merkle_tree(hs, [O.random_matrix(KB, 8, 1), O.random_matrix(KB, 3, 1)])   # 3 is off the ladder of 8
+
+
+def test_fold_matrix_matches_interpolation():
+    # fri/src/two_adic_pcs.rs:108-131 (fold_row by Lagrange interpolation) == fold_matrix, arity 2/4/8
+    f = KB; p = O.prime(f)
+    rng = np.random.default_rng(11)
+    for log_arity in (1, 2, 3):
+        log_len = 6
+        deg = 1 << log_len
+        # a polynomial with EF4 coefficients, evaluated on the subgroup in bit-reversed order
+        coef = rng.integers(0, p, size=(deg, 4), dtype=np.uint32)
+        ev = O.dft_batch(f, coef)                                    # each EF coordinate transformed independently
+        ev = O.reverse_matrix_index_bits(ev)
+        beta = rng.integers(0, p, size=4, dtype=np.uint32)
+        out = O.fold_matrix(f, ev, log_arity, beta)
+        # folding by arity a maps f(x) -> sum_k beta^k f_k(x^a), f_k = coefficients k mod a
+        a = 1 << log_arity
+        bp = [np.array([O.to_monty(f, 1), 0, 0, 0], dtype=np.uint32)]
+        for _ in range(a - 1): bp.append(O.ef_mul(f, bp[-1], beta))
+        folded = np.zeros((deg // a, 4), dtype=np.uint32)
+        for j in range(deg // a):
+            acc = np.zeros(4, dtype=np.uint32)
+            for k in range(a):
+                t = O.ef_mul(f, bp[k], coef[j * a + k])
+                acc = np.array([O.add(f, int(x), int(y)) for x, y in zip(acc, t)], dtype=np.uint32)
+            folded[j] = acc
+        exp = O.reverse_matrix_index_bits(O.dft_batch(f, folded))
+        assert np.array_equal(out, exp)
+
+
+class OracleBackend:
+    """fixture_replay backend built on the C oracle."""
+
+    def __init__(self):
+        rc_i, rc_t, rc_p = FR.fixture_constants()
+        pm = O.make_perm(BB, 16, rc_i, rc_t, rc_p, monty=True)
+        self.hs = O.poseidon2_hasher(pm, pm)
+
+    def lde(self, mat, added_bits, shift): return O.coset_lde_batch(BB, mat, added_bits, shift, bitrev_out=True)
+    def commit(self, mats): return O.merkle_cap(O.merkle_tree(self.hs, mats), 0)
+    def fold(self, vec, log_arity, beta): return O.fold_matrix(BB, vec, log_arity, beta)
+
+
+def test_fixture_replay_with_oracle():
+    """LDE + Merkle + FRI of the oracle reproduce the reference's committed proof bit for bit."""
+    gold = json.loads((GOLD / "uni_stark_two_adic_v1.json").read_text())
+    got = FR.replay(OracleBackend())
+    for k, v in got.items():
+        assert v == gold[k], k
