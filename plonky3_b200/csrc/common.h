@@ -1,0 +1,104 @@
+// Internal declarations shared by the translation units of libp3gpu.
+#pragma once
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <map>
+#include <mutex>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/p3gpu.h"
+#include "field.cuh"
+
+namespace p3 {
+
+void set_error(const char *fmt, ...);
+
+#define P3_CUDA(call)                                                                           \
+    do {                                                                                        \
+        cudaError_t e__ = (call);                                                               \
+        if (e__ != cudaSuccess) {                                                               \
+            p3::set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+            return P3GPU_ECUDA;                                                                 \
+        }                                                                                       \
+    } while (0)
+
+#define P3_CHECK(cond, code, ...)                 \
+    do {                                          \
+        if (!(cond)) {                            \
+            p3::set_error(__VA_ARGS__);           \
+            return (code);                        \
+        }                                         \
+    } while (0)
+
+#define P3_TRY(expr)                      \
+    do {                                  \
+        int32_t rc__ = (expr);            \
+        if (rc__ != P3GPU_OK) return rc__; \
+    } while (0)
+
+struct Poseidon2Consts {          // device layout consumed by the hash kernels
+    u32 rc_init[4 * 24];
+    u32 rc_term[4 * 24];
+    u32 rc_int[32];
+    int rounds_p;
+    int width;
+    int set;
+};
+
+struct TwiddleKey {
+    int field, log_n; u32 shift; int inverse;
+    bool operator<(const TwiddleKey &o) const {
+        return std::tie(field, log_n, shift, inverse) < std::tie(o.field, o.log_n, o.shift, o.inverse);
+    }
+};
+
+}  // namespace p3
+
+struct p3gpu_ctx {
+    int device = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    int sm_count = 148;
+    uint64_t launches = 0;
+    std::mutex mu;
+    // twiddle heaps keyed like the reference's coset_twiddles cache (radix_2_dit_parallel.rs:32-40)
+    std::map<p3::TwiddleKey, uint2 *> twiddles;
+    size_t twiddle_bytes = 0;
+    // FRI half-inverse-power tables (bit-reversed), one per field, grown on demand
+    uint32_t *fold_table[2] = {nullptr, nullptr};
+    size_t fold_table_len[2] = {0, 0};
+    // grow-only scratch
+    void *scratch = nullptr; size_t scratch_bytes = 0;
+    void *scratch2 = nullptr; size_t scratch2_bytes = 0;
+    // Poseidon2 constants: [field][0: width 16, 1: width 24], host copy + device copy
+    p3::Poseidon2Consts p2_host[2][2];
+    p3::Poseidon2Consts *p2_dev = nullptr;  // 4 entries
+};
+
+namespace p3 {
+
+int32_t ctx_scratch(p3gpu_ctx *ctx, size_t bytes, void **out);
+int32_t ctx_scratch2(p3gpu_ctx *ctx, size_t bytes, void **out);
+
+// ntt.cu
+int32_t ntt_dft_batch(p3gpu_ctx *ctx, int field, int kind, const u32 *d_in, u32 *d_out, size_t h, size_t w, u32 shift);
+int32_t ntt_coset_lde(p3gpu_ctx *ctx, int field, const u32 *d_in, size_t h, size_t w, unsigned added_bits, u32 shift,
+                      u32 *d_out, int bitrev_rows);
+// hash.cu
+int32_t hash_poseidon2_permute(p3gpu_ctx *ctx, int field, int width, u32 *d_states, size_t n);
+int32_t hash_keccak_f(p3gpu_ctx *ctx, u64 *d_states, size_t n);
+int32_t hash_merkle_commit(p3gpu_ctx *ctx, int field, int hash, size_t n_mats, const u32 *const *d_mats,
+                           const size_t *heights, const size_t *widths, u32 *d_layers, size_t *layer_lens,
+                           size_t *n_layers);
+// fri.cu
+int32_t fri_fold(p3gpu_ctx *ctx, int field, const u32 *d_in, size_t rows, unsigned log_arity, const u32 beta[4], u32 *d_out);
+
+static inline unsigned log2_floor(size_t x) { unsigned l = 0; while ((x >> l) > 1) l++; return l; }
+static inline bool is_pow2(size_t x) { return x && !(x & (x - 1)); }
+
+}  // namespace p3

@@ -1,0 +1,484 @@
+// Poseidon2 / Keccak-f sponges and the Merkle-tree builder for sm_100a.
+//
+// Replaces MerkleTree::new (merkle-tree/src/merkle_tree.rs:95-178: first_digest_layer :268-338, compress :490-538,
+// compress_and_inject :348-460) with the hash constructions the reference's MerkleTreeMmcs is instantiated with:
+//   Poseidon2 (poseidon2/src/lib.rs:131-147, external.rs:60-159,288-336, monty-31/src/poseidon2.rs:76-85),
+//   PaddingFreeSponge (symmetric/src/sponge.rs:182-216), TruncatedPermutation (symmetric/src/compression.rs:34-49),
+//   KeccakF + SerializingHasher u64 packing (keccak/src/lib.rs:70-76, field/src/integers.rs:494-509),
+//   CompressionFunctionFromHasher (symmetric/src/compression.rs:60-70).
+//
+// Mapping: one sponge per thread (state in registers, rounds fully unrolled, round constants passed as a
+// __grid_constant__ kernel parameter so every constant is an immediate constant-bank operand).  These kernels are
+// integer-ALU bound, not HBM bound: a row of w elements costs ceil(w/RATE) permutations of
+// ~8-12k integer instructions each against w*4 bytes of traffic.
+#include <algorithm>
+#include <cstring>
+
+#include "common.h"
+
+namespace p3 {
+
+// =================================================================================================
+// Poseidon2
+// =================================================================================================
+template <int F> __device__ __forceinline__ u32 sbox(u32 x) {
+    const u32 x2 = mont_mul<F>(x, x);
+    const u32 x3 = mont_mul<F>(x2, x);
+    if (Fp<F>::SBOX_D == 3) return x3;
+    const u32 x4 = mont_mul<F>(x2, x2);
+    return mont_mul<F>(x4, x3);
+}
+
+// poseidon2/src/external.rs:60-74: circ(2,3,1,1)
+template <int F> __device__ __forceinline__ void mat4(u32 &x0, u32 &x1, u32 &x2, u32 &x3) {
+    const u32 t01 = fp_add<F>(x0, x1), t23 = fp_add<F>(x2, x3);
+    const u32 t0123 = fp_add<F>(t01, t23);
+    const u32 t01123 = fp_add<F>(t0123, x1), t01233 = fp_add<F>(t0123, x3);
+    const u32 n3 = fp_add<F>(t01233, fp_double<F>(x0));
+    const u32 n1 = fp_add<F>(t01123, fp_double<F>(x2));
+    const u32 n0 = fp_add<F>(t01123, t01);
+    const u32 n2 = fp_add<F>(t01233, t23);
+    x0 = n0; x1 = n1; x2 = n2; x3 = n3;
+}
+// poseidon2/src/external.rs:113-159
+template <int F, int W> __device__ __forceinline__ void mds_light(u32 (&s)[W]) {
+#pragma unroll
+    for (int i = 0; i < W; i += 4) mat4<F>(s[i], s[i + 1], s[i + 2], s[i + 3]);
+    u32 sums[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        sums[k] = s[k];
+#pragma unroll
+        for (int j = 4; j < W; j += 4) sums[k] = fp_add<F>(sums[k], s[j + k]);
+    }
+#pragma unroll
+    for (int i = 0; i < W; i++) s[i] = fp_add<F>(s[i], sums[i & 3]);
+}
+
+// Internal diagonal V (1 + Diag(V) is the internal matrix): koala-bear/src/poseidon2.rs:407-461,
+// baby-bear/src/poseidon2.rs:394-450.  Encoded as (mul, shift): V_i = mul * 2^shift, shift <= 0.
+struct DiagEntry { int mul, shift; };
+template <int F, int W> struct Diag;
+template <> struct Diag<BABY_BEAR, 16> { static __host__ __device__ constexpr DiagEntry at(int i) {
+    constexpr DiagEntry d[16] = {{-2,0},{1,0},{2,0},{1,-1},{3,0},{4,0},{-1,-1},{-3,0},{-4,0},{1,-8},{1,-2},{1,-3},{1,-27},{-1,-8},{-1,-4},{-1,-27}};
+    return d[i]; } };
+template <> struct Diag<BABY_BEAR, 24> { static __host__ __device__ constexpr DiagEntry at(int i) {
+    constexpr DiagEntry d[24] = {{-2,0},{1,0},{2,0},{1,-1},{3,0},{4,0},{-1,-1},{-3,0},{-4,0},{1,-8},{1,-2},{1,-3},{1,-4},{1,-7},{1,-9},{1,-27},{-1,-8},{-1,-2},{-1,-3},{-1,-4},{-1,-5},{-1,-6},{-1,-7},{-1,-27}};
+    return d[i]; } };
+template <> struct Diag<KOALA_BEAR, 16> { static __host__ __device__ constexpr DiagEntry at(int i) {
+    constexpr DiagEntry d[16] = {{-2,0},{1,0},{2,0},{1,-1},{3,0},{4,0},{-1,-1},{-3,0},{-4,0},{1,-8},{1,-3},{1,-24},{-1,-8},{-1,-3},{-1,-4},{-1,-24}};
+    return d[i]; } };
+template <> struct Diag<KOALA_BEAR, 24> { static __host__ __device__ constexpr DiagEntry at(int i) {
+    constexpr DiagEntry d[24] = {{-2,0},{1,0},{2,0},{1,-1},{3,0},{4,0},{-1,-1},{-3,0},{-4,0},{1,-8},{1,-2},{1,-3},{1,-4},{1,-5},{1,-6},{1,-24},{-1,-8},{-1,-3},{-1,-4},{-1,-5},{-1,-6},{-1,-7},{-1,-9},{-1,-24}};
+    return d[i]; } };
+
+// x * 2^-k for a Montgomery value x: redc(x << (32-k)) = x * 2^(32-k) * 2^-32  (monty-31 div_2exp_u64)
+template <int F, int K> __device__ __forceinline__ u32 div_2exp(u32 x) {
+    return mont_redc<F>((u64)x << (32 - K));
+}
+template <int F, int W, int I> __device__ __forceinline__ u32 diag_mul_add(u32 x, u32 sum) {
+    constexpr DiagEntry d = Diag<F, W>::at(I);
+    constexpr int am = d.mul < 0 ? -d.mul : d.mul;
+    u32 v;
+    if (d.shift == 0) {
+        v = x;
+        if (am == 2) v = fp_double<F>(x);
+        if (am == 3) v = fp_add<F>(fp_double<F>(x), x);
+        if (am == 4) v = fp_double<F>(fp_double<F>(x));
+    } else if (d.shift == -1) {
+        v = fp_halve<F>(x);
+    } else {
+        v = div_2exp<F, -d.shift>(x);
+    }
+    return d.mul < 0 ? fp_sub<F>(sum, v) : fp_add<F>(sum, v);
+}
+template <int F, int W, int I> struct DiagLoop {
+    static __device__ __forceinline__ void run(u32 (&s)[W], u32 sum) {
+        s[I] = diag_mul_add<F, W, I>(s[I], sum);
+        DiagLoop<F, W, I + 1>::run(s, sum);
+    }
+};
+template <int F, int W> struct DiagLoop<F, W, W> { static __device__ __forceinline__ void run(u32 (&)[W], u32) {} };
+
+template <int F, int W>
+__device__ __forceinline__ void poseidon2_permute(u32 (&s)[W], const Poseidon2Consts &k) {
+    mds_light<F, W>(s);
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+#pragma unroll
+        for (int i = 0; i < W; i++) s[i] = sbox<F>(fp_add<F>(s[i], k.rc_init[r * W + i]));
+        mds_light<F, W>(s);
+    }
+    // monty-31/src/poseidon2.rs:76-85
+#pragma unroll 1
+    for (int r = 0; r < k.rounds_p; r++) {
+        s[0] = sbox<F>(fp_add<F>(s[0], k.rc_int[r]));
+        u32 part = s[1];
+#pragma unroll
+        for (int i = 2; i < W; i++) part = fp_add<F>(part, s[i]);
+        const u32 sum = fp_add<F>(part, s[0]);
+        s[0] = fp_sub<F>(part, s[0]);
+        DiagLoop<F, W, 1>::run(s, sum);
+    }
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+#pragma unroll
+        for (int i = 0; i < W; i++) s[i] = sbox<F>(fp_add<F>(s[i], k.rc_term[r * W + i]));
+        mds_light<F, W>(s);
+    }
+}
+
+template <int F, int W>
+__global__ void __launch_bounds__(128) poseidon2_permute_kernel(u32 *states, size_t n, const __grid_constant__ Poseidon2Consts k) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n) return;
+    u32 s[W];
+#pragma unroll
+    for (int i = 0; i < W; i++) s[i] = states[idx * W + i];
+    poseidon2_permute<F, W>(s, k);
+#pragma unroll
+    for (int i = 0; i < W; i++) states[idx * W + i] = s[i];
+}
+
+// ---- leaf sponge ---------------------------------------------------------------------------------
+constexpr int MAX_MATS = 8;
+struct LeafArgs {
+    const u32 *ptr[MAX_MATS];
+    u32 width[MAX_MATS];
+    int n_mats;
+    size_t height;
+    u32 *out;  // height x 8
+};
+
+// streaming cursor over the concatenation of row r of every matrix (input order; merkle_tree.rs:312-316)
+struct RowCursor {
+    const LeafArgs &a; size_t row; int m; u32 col; const u32 *p;
+    __device__ __forceinline__ RowCursor(const LeafArgs &a_, size_t r) : a(a_), row(r), m(0), col(0), p(nullptr) { settle(); }
+    __device__ __forceinline__ void settle() {
+        while (m < a.n_mats && col >= a.width[m]) { m++; col = 0; }
+        if (m < a.n_mats) p = a.ptr[m] + row * a.width[m];
+    }
+    __device__ __forceinline__ bool more() const { return m < a.n_mats; }
+    __device__ __forceinline__ u32 next() { u32 v = __ldg(p + col); col++; if (col >= a.width[m]) settle(); return v; }
+};
+
+template <int F, int W>
+__global__ void __launch_bounds__(128) poseidon2_leaf_kernel(const __grid_constant__ LeafArgs a, const __grid_constant__ Poseidon2Consts k) {
+    constexpr int RATE = W - 8;
+    const size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= a.height) return;
+    u32 s[W];
+#pragma unroll
+    for (int i = 0; i < W; i++) s[i] = 0;
+    if (a.n_mats == 1) {  // fast path: one matrix, contiguous row
+        const u32 w = a.width[0];
+        const u32 *row = a.ptr[0] + r * w;
+        u32 c0 = 0;
+        for (; c0 + RATE <= w; c0 += RATE) {
+#pragma unroll
+            for (int i = 0; i < RATE; i++) s[i] = __ldg(row + c0 + i);
+            poseidon2_permute<F, W>(s, k);
+        }
+        if (c0 < w) {
+#pragma unroll
+            for (int i = 0; i < RATE; i++) if (c0 + i < w) s[i] = __ldg(row + c0 + i);
+            poseidon2_permute<F, W>(s, k);
+        }
+    } else {
+        RowCursor cur(a, r);
+        while (cur.more()) {
+#pragma unroll
+            for (int i = 0; i < RATE; i++) if (cur.more()) s[i] = cur.next();
+            poseidon2_permute<F, W>(s, k);
+        }
+    }
+    uint4 *o = reinterpret_cast<uint4 *>(a.out + r * 8);
+    o[0] = make_uint4(s[0], s[1], s[2], s[3]);
+    o[1] = make_uint4(s[4], s[5], s[6], s[7]);
+}
+
+// out[i] = perm16(left || right)[..8].  right == nullptr-equivalents are handled by the caller through `rmode`:
+//   rmode 0: children are in[2i], in[2i+1]  (compress, merkle_tree.rs:490-538)
+//   rmode 1: left = io[i] (in place), right = (i < inj_h ? inj[i] : 0)   (second compress of compress_and_inject)
+template <int F>
+__global__ void __launch_bounds__(128) poseidon2_compress_kernel(const u32 *in, const u32 *inj, size_t inj_h, u32 *out, size_t n, int rmode,
+                                                                 const __grid_constant__ Poseidon2Consts k) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    u32 s[16];
+    const uint4 *l = reinterpret_cast<const uint4 *>(rmode == 0 ? in + 16 * i : out + 8 * i);
+    uint4 a = l[0], b = l[1], c, d;
+    if (rmode == 0) { c = l[2]; d = l[3]; }
+    else if (i < inj_h) { const uint4 *rp = reinterpret_cast<const uint4 *>(inj + 8 * i); c = rp[0]; d = rp[1]; }
+    else { c = make_uint4(0, 0, 0, 0); d = c; }
+    s[0] = a.x; s[1] = a.y; s[2] = a.z; s[3] = a.w; s[4] = b.x; s[5] = b.y; s[6] = b.z; s[7] = b.w;
+    s[8] = c.x; s[9] = c.y; s[10] = c.z; s[11] = c.w; s[12] = d.x; s[13] = d.y; s[14] = d.z; s[15] = d.w;
+    poseidon2_permute<F, 16>(s, k);
+    uint4 *o = reinterpret_cast<uint4 *>(out + 8 * i);
+    o[0] = make_uint4(s[0], s[1], s[2], s[3]);
+    o[1] = make_uint4(s[4], s[5], s[6], s[7]);
+}
+
+// =================================================================================================
+// Keccak-f[1600]
+// =================================================================================================
+__constant__ u64 KECCAK_RC[24] = {
+    0x0000000000000001ULL, 0x0000000000008082ULL, 0x800000000000808aULL, 0x8000000080008000ULL, 0x000000000000808bULL,
+    0x0000000080000001ULL, 0x8000000080008081ULL, 0x8000000000008009ULL, 0x000000000000008aULL, 0x0000000000000088ULL,
+    0x0000000080008009ULL, 0x000000008000000aULL, 0x000000008000808bULL, 0x800000000000008bULL, 0x8000000000008089ULL,
+    0x8000000000008003ULL, 0x8000000000008002ULL, 0x8000000000000080ULL, 0x000000000000800aULL, 0x800000008000000aULL,
+    0x8000000080008081ULL, 0x8000000000008080ULL, 0x0000000080000001ULL, 0x8000000080008008ULL};
+
+__device__ __forceinline__ u64 rotl64(u64 x, int r) { return (x << r) | (x >> (64 - r)); }
+
+__device__ __forceinline__ void keccak_f(u64 (&a)[25]) {
+#pragma unroll 1
+    for (int round = 0; round < 24; round++) {
+        u64 c[5], d[5];
+#pragma unroll
+        for (int x = 0; x < 5; x++) c[x] = a[x] ^ a[x + 5] ^ a[x + 10] ^ a[x + 15] ^ a[x + 20];
+#pragma unroll
+        for (int x = 0; x < 5; x++) d[x] = c[(x + 4) % 5] ^ rotl64(c[(x + 1) % 5], 1);
+#pragma unroll
+        for (int i = 0; i < 25; i++) a[i] ^= d[i % 5];
+        // rho + pi
+        u64 b[25];
+        b[0] = a[0];
+        b[10] = rotl64(a[1], 1);   b[20] = rotl64(a[2], 62);  b[5] = rotl64(a[3], 28);   b[15] = rotl64(a[4], 27);
+        b[16] = rotl64(a[5], 36);  b[1] = rotl64(a[6], 44);   b[11] = rotl64(a[7], 6);   b[21] = rotl64(a[8], 55);
+        b[6] = rotl64(a[9], 20);   b[7] = rotl64(a[10], 3);   b[17] = rotl64(a[11], 10); b[2] = rotl64(a[12], 43);
+        b[12] = rotl64(a[13], 25); b[22] = rotl64(a[14], 39); b[23] = rotl64(a[15], 41); b[8] = rotl64(a[16], 45);
+        b[18] = rotl64(a[17], 15); b[3] = rotl64(a[18], 21);  b[13] = rotl64(a[19], 8);  b[14] = rotl64(a[20], 18);
+        b[24] = rotl64(a[21], 2);  b[9] = rotl64(a[22], 61);  b[19] = rotl64(a[23], 56); b[4] = rotl64(a[24], 14);
+#pragma unroll
+        for (int y = 0; y < 5; y++)
+#pragma unroll
+            for (int x = 0; x < 5; x++) a[x + 5 * y] = b[x + 5 * y] ^ (~b[(x + 1) % 5 + 5 * y] & b[(x + 2) % 5 + 5 * y]);
+        a[0] ^= KECCAK_RC[round];
+    }
+}
+
+__global__ void __launch_bounds__(128) keccak_f_kernel(u64 *states, size_t n) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n) return;
+    u64 a[25];
+#pragma unroll
+    for (int i = 0; i < 25; i++) a[i] = states[idx * 25 + i];
+    keccak_f(a);
+#pragma unroll
+    for (int i = 0; i < 25; i++) states[idx * 25 + i] = a[i];
+}
+
+// leaf = SerializingHasher<PaddingFreeSponge<KeccakF,25,17,4>>: u32 pairs -> u64 words over the concatenated row stream
+// (field/src/integers.rs:494-509), overwrite-absorb 17 words per permutation (sponge.rs:182-216).
+__global__ void __launch_bounds__(128) keccak_leaf_kernel(const __grid_constant__ LeafArgs a) {
+    const size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= a.height) return;
+    u64 s[25];
+#pragma unroll
+    for (int i = 0; i < 25; i++) s[i] = 0;
+    if (a.n_mats == 1) {
+        const u32 w = a.width[0];
+        const u32 *row = a.ptr[0] + r * w;
+        u32 c0 = 0;
+        for (; c0 + 34 <= w; c0 += 34) {
+#pragma unroll
+            for (int i = 0; i < 17; i++) s[i] = (u64)__ldg(row + c0 + 2 * i) | ((u64)__ldg(row + c0 + 2 * i + 1) << 32);
+            keccak_f(s);
+        }
+        if (c0 < w) {
+#pragma unroll
+            for (int i = 0; i < 17; i++) {
+                const u32 e = c0 + 2 * i;
+                if (e < w) s[i] = (u64)__ldg(row + e) | (e + 1 < w ? ((u64)__ldg(row + e + 1) << 32) : 0ull);
+            }
+            keccak_f(s);
+        }
+    } else {
+        RowCursor cur(a, r);
+        while (cur.more()) {
+#pragma unroll
+            for (int i = 0; i < 17; i++) {
+                if (cur.more()) {
+                    const u64 lo = cur.next();
+                    const u64 hi = cur.more() ? (u64)cur.next() : 0ull;
+                    s[i] = lo | (hi << 32);
+                }
+            }
+            keccak_f(s);
+        }
+    }
+    u64 *o = reinterpret_cast<u64 *>(a.out + r * 8);
+    o[0] = s[0]; o[1] = s[1]; o[2] = s[2]; o[3] = s[3];
+}
+
+// node = CompressionFunctionFromHasher<sponge,2,4>: 8 words < rate 17 -> exactly one permutation (compression.rs:60-70)
+__global__ void __launch_bounds__(128) keccak_compress_kernel(const u32 *in, const u32 *inj, size_t inj_h, u32 *out, size_t n, int rmode) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    u64 s[25];
+#pragma unroll
+    for (int j = 0; j < 25; j++) s[j] = 0;
+    const u64 *l = reinterpret_cast<const u64 *>(rmode == 0 ? in + 16 * i : out + 8 * i);
+    s[0] = l[0]; s[1] = l[1]; s[2] = l[2]; s[3] = l[3];
+    if (rmode == 0) { s[4] = l[4]; s[5] = l[5]; s[6] = l[6]; s[7] = l[7]; }
+    else if (i < inj_h) { const u64 *rp = reinterpret_cast<const u64 *>(inj + 8 * i); s[4] = rp[0]; s[5] = rp[1]; s[6] = rp[2]; s[7] = rp[3]; }
+    keccak_f(s);
+    u64 *o = reinterpret_cast<u64 *>(out + 8 * i);
+    o[0] = s[0]; o[1] = s[1]; o[2] = s[2]; o[3] = s[3];
+}
+
+// =================================================================================================
+// host side
+// =================================================================================================
+static inline unsigned nblocks(size_t n, unsigned t) { return (unsigned)((n + t - 1) / t); }
+
+static int32_t get_consts(p3gpu_ctx *ctx, int field, int width, const Poseidon2Consts **out) {
+    P3_CHECK(field == BABY_BEAR || field == KOALA_BEAR, P3GPU_EUNSUPPORTED, "unknown field %d", field);
+    P3_CHECK(width == 16 || width == 24, P3GPU_EUNSUPPORTED, "Poseidon2 width %d unsupported (16 or 24)", width);
+    const Poseidon2Consts *k = &ctx->p2_host[field][width == 24];
+    P3_CHECK(k->set, P3GPU_ESTATE, "Poseidon2 constants for field %d width %d not set (p3gpu_poseidon2_set_constants)", field, width);
+    *out = k;
+    return P3GPU_OK;
+}
+
+int32_t hash_poseidon2_permute(p3gpu_ctx *ctx, int field, int width, u32 *d_states, size_t n) {
+    const Poseidon2Consts *k;
+    P3_TRY(get_consts(ctx, field, width, &k));
+    if (n == 0) return P3GPU_OK;
+    const unsigned g = nblocks(n, 128);
+    if (field == BABY_BEAR && width == 16) poseidon2_permute_kernel<BABY_BEAR, 16><<<g, 128, 0, ctx->stream>>>(d_states, n, *k);
+    else if (field == BABY_BEAR) poseidon2_permute_kernel<BABY_BEAR, 24><<<g, 128, 0, ctx->stream>>>(d_states, n, *k);
+    else if (width == 16) poseidon2_permute_kernel<KOALA_BEAR, 16><<<g, 128, 0, ctx->stream>>>(d_states, n, *k);
+    else poseidon2_permute_kernel<KOALA_BEAR, 24><<<g, 128, 0, ctx->stream>>>(d_states, n, *k);
+    ctx->launches++;
+    P3_CUDA(cudaGetLastError());
+    return P3GPU_OK;
+}
+
+int32_t hash_keccak_f(p3gpu_ctx *ctx, u64 *d_states, size_t n) {
+    if (n == 0) return P3GPU_OK;
+    keccak_f_kernel<<<nblocks(n, 128), 128, 0, ctx->stream>>>(d_states, n);
+    ctx->launches++;
+    P3_CUDA(cudaGetLastError());
+    return P3GPU_OK;
+}
+
+static int32_t launch_leaf(p3gpu_ctx *ctx, int field, int hash, const LeafArgs &a) {
+    if (a.height == 0) return P3GPU_OK;
+    const unsigned g = nblocks(a.height, 128);
+    if (hash == P3GPU_HASH_KECCAK) {
+        keccak_leaf_kernel<<<g, 128, 0, ctx->stream>>>(a);
+    } else {
+        const Poseidon2Consts *k;
+        P3_TRY(get_consts(ctx, field, hash == P3GPU_HASH_POSEIDON2_W24 ? 24 : 16, &k));
+        if (field == BABY_BEAR && hash == P3GPU_HASH_POSEIDON2_W16) poseidon2_leaf_kernel<BABY_BEAR, 16><<<g, 128, 0, ctx->stream>>>(a, *k);
+        else if (field == BABY_BEAR) poseidon2_leaf_kernel<BABY_BEAR, 24><<<g, 128, 0, ctx->stream>>>(a, *k);
+        else if (hash == P3GPU_HASH_POSEIDON2_W16) poseidon2_leaf_kernel<KOALA_BEAR, 16><<<g, 128, 0, ctx->stream>>>(a, *k);
+        else poseidon2_leaf_kernel<KOALA_BEAR, 24><<<g, 128, 0, ctx->stream>>>(a, *k);
+    }
+    ctx->launches++;
+    P3_CUDA(cudaGetLastError());
+    return P3GPU_OK;
+}
+
+static int32_t launch_compress(p3gpu_ctx *ctx, int field, int hash, const u32 *in, const u32 *inj, size_t inj_h, u32 *out, size_t n, int rmode) {
+    if (n == 0) return P3GPU_OK;
+    const unsigned g = nblocks(n, 128);
+    if (hash == P3GPU_HASH_KECCAK) {
+        keccak_compress_kernel<<<g, 128, 0, ctx->stream>>>(in, inj, inj_h, out, n, rmode);
+    } else {
+        const Poseidon2Consts *k;
+        P3_TRY(get_consts(ctx, field, 16, &k));
+        if (field == BABY_BEAR) poseidon2_compress_kernel<BABY_BEAR><<<g, 128, 0, ctx->stream>>>(in, inj, inj_h, out, n, rmode, *k);
+        else poseidon2_compress_kernel<KOALA_BEAR><<<g, 128, 0, ctx->stream>>>(in, inj, inj_h, out, n, rmode, *k);
+    }
+    ctx->launches++;
+    P3_CUDA(cudaGetLastError());
+    return P3GPU_OK;
+}
+
+static size_t next_pow2(size_t x) { size_t p = 1; while (p < x) p <<= 1; return p; }
+static size_t padded_len2(size_t raw) { return raw <= 1 ? raw : (raw + 1) / 2 * 2; }  // merkle_tree.rs:473-481, N = 2
+
+// mmcs/geometry.rs:83-124
+static int32_t validate_heights(const size_t *hs, size_t n) {
+    size_t maxh = 0;
+    for (size_t i = 0; i < n; i++) maxh = std::max(maxh, hs[i]);
+    P3_CHECK(maxh > 0, P3GPU_EINVAL, "all matrices have height 0");
+    unsigned lmax = 0;
+    while (((size_t)1 << lmax) < maxh) lmax++;
+    for (size_t i = 0; i < n; i++) {
+        unsigned l = 0;
+        while (((size_t)1 << l) < hs[i]) l++;
+        const size_t expect = hs[i] == 0 ? 1 : ((maxh - 1) >> (lmax - l)) + 1;
+        P3_CHECK(hs[i] == expect, P3GPU_EINVAL, "matrix height %zu incompatible with tallest height %zu: expected %zu", hs[i], maxh, expect);
+    }
+    return P3GPU_OK;
+}
+
+int32_t hash_merkle_commit(p3gpu_ctx *ctx, int field, int hash, size_t n_mats, const u32 *const *d_mats, const size_t *heights,
+                           const size_t *widths, u32 *d_layers, size_t *layer_lens, size_t *n_layers_out) {
+    P3_CHECK(hash >= P3GPU_HASH_POSEIDON2_W16 && hash <= P3GPU_HASH_KECCAK, P3GPU_EUNSUPPORTED, "unknown hash %d", hash);
+    P3_CHECK(n_mats >= 1, P3GPU_EINVAL, "No matrices given?");
+    P3_TRY(validate_heights(heights, n_mats));
+    for (size_t i = 0; i < n_mats; i++) P3_CHECK(widths[i] < (1ull << 31), P3GPU_EINVAL, "matrix width too large");
+    // stable sort by height, tallest first (merkle_tree.rs:124-127)
+    std::vector<size_t> order(n_mats);
+    for (size_t i = 0; i < n_mats; i++) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](size_t x, size_t y) { return heights[x] > heights[y]; });
+    const size_t max_h = heights[order[0]];
+
+    auto fill_leaf = [&](size_t begin, size_t end, size_t h, u32 *out, LeafArgs &la) -> int32_t {
+        P3_CHECK(end - begin <= (size_t)MAX_MATS, P3GPU_EUNSUPPORTED, "more than %d matrices of one height in a batch", MAX_MATS);
+        memset(&la, 0, sizeof la);
+        la.n_mats = 0;
+        for (size_t k = begin; k < end; k++) {
+            if (widths[order[k]] == 0) continue;  // contributes nothing to the stream
+            la.ptr[la.n_mats] = d_mats[order[k]];
+            la.width[la.n_mats] = (u32)widths[order[k]];
+            la.n_mats++;
+        }
+        la.height = h; la.out = out;
+        return P3GPU_OK;
+    };
+
+    size_t next = 0;
+    while (next < n_mats && heights[order[next]] == max_h) next++;
+    size_t n_layers = 0;
+    u32 *cur = d_layers;
+    size_t cur_len = padded_len2(max_h);
+    if (cur_len > max_h) P3_CUDA(cudaMemsetAsync(cur + max_h * 8, 0, (cur_len - max_h) * 32, ctx->stream));
+    {
+        LeafArgs la;
+        P3_TRY(fill_leaf(0, next, max_h, cur, la));
+        P3_TRY(launch_leaf(ctx, field, hash, la));
+    }
+    layer_lens[n_layers++] = cur_len;
+    while (cur_len > 1) {
+        const size_t raw_next = cur_len / 2;
+        const size_t next_layer_len = next_pow2(raw_next);
+        const size_t inj_begin = next;
+        while (next < n_mats && next_pow2(heights[order[next]]) == next_layer_len) next++;
+        const size_t out_len = padded_len2(raw_next);
+        u32 *out = cur + cur_len * 8;
+        if (out_len > raw_next) P3_CUDA(cudaMemsetAsync(out + raw_next * 8, 0, (out_len - raw_next) * 32, ctx->stream));
+        P3_TRY(launch_compress(ctx, field, hash, cur, nullptr, 0, out, raw_next, 0));
+        if (next > inj_begin) {  // compress_and_inject (merkle_tree.rs:348-460)
+            const size_t inj_h = heights[order[inj_begin]];
+            void *rd = nullptr;
+            P3_TRY(ctx_scratch2(ctx, inj_h * 32, &rd));
+            LeafArgs la;
+            P3_TRY(fill_leaf(inj_begin, next, inj_h, (u32 *)rd, la));
+            P3_TRY(launch_leaf(ctx, field, hash, la));
+            P3_TRY(launch_compress(ctx, field, hash, nullptr, (const u32 *)rd, inj_h, out, raw_next, 1));
+        }
+        P3_CHECK(n_layers < 64, P3GPU_EINVAL, "too many layers");
+        layer_lens[n_layers++] = out_len;
+        cur = out; cur_len = out_len;
+    }
+    *n_layers_out = n_layers;
+    return P3GPU_OK;
+}
+
+}  // namespace p3

@@ -1,0 +1,146 @@
+"""FRI prover-side surface on the GPU: FriParameters + compute_log_arity_for_round (fri/src/config.rs:10-207),
+TwoAdicFriFolding.fold_matrix (fri/src/two_adic_pcs.rs:134-213), commit_phase (fri/src/prover.rs:192-286) and
+TwoAdicFriPcs.commit (fri/src/two_adic_pcs.rs:300-363).  The Fiat-Shamir challenger stays on the host: per round only
+the Merkle cap crosses PCIe (<= 2^cap_height x 32 bytes)."""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import List, Optional
+
+import numpy as np
+
+from .dft import Radix2DitParallel, _log2_strict, reverse_matrix_index_bits
+from .field import Field
+from .gpu import _is_torch
+from .merkle_tree import MerkleTreeMmcs
+
+
+@dataclass
+class FriParameters:
+    """fri/src/config.rs:10-23."""
+    log_blowup: int
+    log_final_poly_len: int
+    max_log_arity: int
+    num_queries: int
+    commit_proof_of_work_bits: int
+    query_proof_of_work_bits: int
+    mmcs: MerkleTreeMmcs
+
+    def blowup(self): return 1 << self.log_blowup
+    def final_poly_len(self): return 1 << self.log_final_poly_len
+
+    @classmethod
+    def new_testing(cls, mmcs, log_final_poly_len):  # config.rs:76-86
+        return cls(2, log_final_poly_len, 1, 2, 1, 1, mmcs)
+
+    @classmethod
+    def new_benchmark(cls, mmcs):  # config.rs:104-114
+        return cls(1, 0, 1, 100, 0, 16, mmcs)
+
+    @classmethod
+    def new_benchmark_high_arity(cls, mmcs):  # config.rs:118-128
+        return cls(1, 0, 3, 100, 0, 16, mmcs)
+
+
+def compute_log_arity_for_round(log_current_height, next_input_log_height, log_final_height, max_log_arity):
+    """fri/src/config.rs:180-207."""
+    if max_log_arity <= 0:
+        raise ValueError("max_log_arity must be at least 1 to guarantee folding progress")
+    max_fold = log_current_height - log_final_height
+    if next_input_log_height is not None:
+        max_fold = min(max_fold, log_current_height - next_input_log_height)
+    return min(max_fold, max_log_arity)
+
+
+class TwoAdicFriFolding:
+    """FriFoldingStrategy for the two-adic PCS (two_adic_pcs.rs:92-213)."""
+
+    def __init__(self, field: Field, gpu):
+        self.field, self.gpu = field, gpu
+
+    def extra_query_index_bits(self): return 0
+
+    def fold_matrix(self, beta, log_arity: int, m):
+        """m: (rows, arity*4) base matrix = rows x arity EF4 values, bit-reversed order -> (rows, 4)."""
+        return self.gpu.fri_fold(self.field.id, m, log_arity, beta)
+
+
+@dataclass
+class CommitPhaseResult:
+    commits: list
+    data: list
+    log_arities: List[int]
+    pow_witnesses: list
+    final_poly: np.ndarray
+
+
+def commit_phase(folding: TwoAdicFriFolding, params: FriParameters, inputs: list, challenger, dft: Radix2DitParallel) -> CommitPhaseResult:
+    """fri/src/prover.rs:192-286.  inputs: EF4 vectors ((len,4) arrays/tensors) sorted by descending length, bit-reversed.
+    challenger protocol: observe_cap(cap), grind(bits) -> witness, sample_algebra_element() -> 4 Montgomery words,
+    observe_algebra_slice(vec)."""
+    if params.max_log_arity <= 0:
+        raise ValueError("max_log_arity must be at least 1 to guarantee folding progress")
+    inputs = list(inputs)
+    folded = inputs.pop(0)
+    commits, data, log_arities, pow_witnesses = [], [], [], []
+    log_final_height = params.log_blowup + params.log_final_poly_len
+    field = folding.field
+    while folded.shape[0] > params.blowup() * params.final_poly_len():
+        log_cur = _log2_strict(int(folded.shape[0]))
+        nxt = _log2_strict(int(inputs[0].shape[0])) if inputs else None
+        log_arity = compute_log_arity_for_round(log_cur, nxt, log_final_height, params.max_log_arity)
+        log_arities.append(log_arity)
+        leaves = folded.reshape(folded.shape[0] >> log_arity, 4 << log_arity)      # RowMajorMatrix::new(folded, arity) + ExtensionMmcs
+        commit, prover_data = params.mmcs.commit_matrix(leaves)
+        challenger.observe_cap(commit)
+        commits.append(commit)
+        pow_witnesses.append(challenger.grind(params.commit_proof_of_work_bits))
+        beta = np.asarray(challenger.sample_algebra_element(), dtype=np.uint32)
+        folded = folding.fold_matrix(beta, log_arity, leaves)
+        data.append(prover_data)
+        if inputs and inputs[0].shape[0] == folded.shape[0]:
+            # folded += beta^arity * input  (prover.rs:258-265); tiny host-side EF op kept on the host for generality
+            raise NotImplementedError("multiple FRI input heights: roll-in of shorter inputs is a §8(f) 'next' item")
+    fl = params.final_poly_len()
+    final = folded[:fl]
+    final = final.cpu().numpy().view(np.uint32) if _is_torch(final) else np.array(final, dtype=np.uint32)
+    if fl > 1:
+        final = dft.idft_algebra_batch(reverse_matrix_index_bits(final.reshape(fl, 4)).reshape(fl, 1, 4)).reshape(fl, 4)
+    challenger.observe_algebra_slice(final)
+    return CommitPhaseResult(commits, data, log_arities, pow_witnesses, final)
+
+
+class TwoAdicFriPcs:
+    """TwoAdicFriPcs<Val, Dft, InputMmcs, FriMmcs> — commit side (two_adic_pcs.rs:261-363)."""
+
+    def __init__(self, dft: Radix2DitParallel, mmcs: MerkleTreeMmcs, fri: FriParameters):
+        self.dft, self.mmcs, self.fri = dft, mmcs, fri
+
+    def natural_domain_for_degree(self, degree: int):
+        return (self.dft.field.ONE, _log2_strict(degree))      # (shift, log_size): TwoAdicMultiplicativeCoset
+
+    def commit(self, evaluations: list):
+        """evaluations: list of ((shift, log_size), matrix).  LDE onto GENERATOR*K, bit-reversed rows, MMCS commit."""
+        f = self.dft.field
+        ldes = []
+        for (dshift, log_size), evals in evaluations:
+            assert (1 << log_size) == evals.shape[0]
+            shift = f.div(f.generator, dshift)                   # two_adic_pcs.rs:312
+            ldes.append(self.dft.coset_lde_batch(evals, self.fri.log_blowup, shift).bit_reverse_rows())
+        return self.mmcs.commit(ldes)
+
+    def commit_ldes(self, ldes: list):
+        min_height = 1 << self.fri.log_blowup
+        for lde in ldes:
+            if lde.shape[0] < min_height:
+                raise ValueError(f"committed LDE height {lde.shape[0]} is smaller than the blowup factor {min_height}")
+        return self.mmcs.commit(ldes)
+
+    def get_evaluations_on_domain(self, prover_data, idx: int, domain):
+        """two_adic_pcs.rs:376-385 fast path: first |domain| rows of the committed bit-reversed LDE."""
+        shift, log_size = domain
+        lde = self.mmcs.get_matrices(prover_data)[idx]
+        if shift == self.dft.field.generator and lde.shape[0] >= (1 << log_size):
+            from .dft import BitReversedMatrixView
+            return BitReversedMatrixView(lde[: 1 << log_size])
+        raise NotImplementedError("re-evaluation on a foreign coset (two_adic_pcs.rs:390-403) is host-side in this round")

@@ -1,0 +1,110 @@
+"""MerkleTreeMmcs on the GPU: mirrors merkle-tree/src/mmcs/mod.rs:71 + mmcs/batch.rs:22-128 (Mmcs impl) and
+merkle_tree.rs:33-217 (MerkleTree).  commit runs on the device; get_matrices/open_batch are host-side pointer chasing
+over the stored digest layers, as in the reference."""
+from __future__ import annotations
+
+from dataclasses import dataclass, field as dc_field
+from typing import List, Optional
+
+import numpy as np
+
+from . import _lib
+from .field import Field
+from .gpu import Gpu, default_gpu, _is_torch
+from .poseidon2 import Poseidon2
+
+
+def _log2_ceil(n: int) -> int:
+    return max(n - 1, 0).bit_length()
+
+
+@dataclass
+class MerkleTree:
+    """merkle_tree.rs:33-69: leaves (insertion order), every digest layer, arity schedule (always 2 here)."""
+    leaves: list
+    digest_layers: list          # layer 0 = leaf digests ... last = [root]; each (len, 8)
+    arity_schedule: List[int] = dc_field(default_factory=list)
+
+    def root(self):
+        return _host(self.digest_layers[-1][0:1])[0]
+
+    def cap(self, cap_height: int):
+        """merkle_tree.rs:198-217."""
+        n = len(self.digest_layers)
+        if cap_height >= n:
+            raise ValueError(f"cap_height {cap_height} exceeds tree depth {n}")
+        layer = self.digest_layers[n - 1 - cap_height]
+        return _host(layer[: min(1 << cap_height, layer.shape[0])])
+
+    def num_layers(self):
+        return len(self.digest_layers)
+
+
+def _host(x):
+    if _is_torch(x):
+        return x.cpu().numpy().view(np.uint32)
+    return np.array(x, dtype=np.uint32)
+
+
+class MerkleTreeMmcs:
+    """MerkleTreeMmcs<P, PW, H, C, 2, 8>.
+
+    hash configurations (examples/src/types.rs:19-53, merkle-tree/benches/merkle_tree.rs:38):
+      MerkleTreeMmcs.poseidon2(perm16)            leaf PaddingFreeSponge<Perm16,16,8,8>,  node TruncatedPermutation<Perm16,2,8,16>
+      MerkleTreeMmcs.poseidon2(perm16, perm24)    leaf PaddingFreeSponge<Perm24,24,16,8>, node TruncatedPermutation<Perm16,2,8,16>
+      MerkleTreeMmcs.keccak(field)                leaf SerializingHasher<PaddingFreeSponge<KeccakF,25,17,4>>, node CompressionFunctionFromHasher
+    """
+
+    def __init__(self, field: Field, hash_kind: int, cap_height: int = 0, gpu: Optional[Gpu] = None, perms=()):
+        self.field, self.hash_kind, self.cap_height = field, hash_kind, cap_height
+        self.gpu = gpu or default_gpu()
+        self.perms = perms
+
+    @classmethod
+    def poseidon2(cls, perm16: Poseidon2, perm24: Optional[Poseidon2] = None, cap_height: int = 0, gpu=None):
+        assert perm16.width == 16 and (perm24 is None or perm24.width == 24)
+        kind = _lib.HASH_POSEIDON2_W24 if perm24 is not None else _lib.HASH_POSEIDON2_W16
+        return cls(perm16.field, kind, cap_height, gpu, tuple(p for p in (perm16, perm24) if p is not None))
+
+    @classmethod
+    def keccak(cls, field: Field, cap_height: int = 0, gpu=None):
+        return cls(field, _lib.HASH_KECCAK, cap_height, gpu)
+
+    # commit/src/mmcs.rs:42, merkle-tree/src/mmcs/batch.rs:42-64
+    def commit(self, inputs: list):
+        if len(inputs) == 0:
+            raise _lib.P3GpuError("No matrices given?")
+        for p in self.perms:
+            p.upload(self.gpu)
+        layers = self.gpu.merkle_commit(self.field.id, self.hash_kind, inputs)
+        tree = MerkleTree(list(inputs), layers, [2] * (len(layers) - 1))
+        eff = min(self.cap_height, max(tree.num_layers() - 1, 0))
+        return tree.cap(eff), tree
+
+    def commit_matrix(self, m):
+        return self.commit([m])
+
+    # commit/src/mmcs.rs:106
+    def get_matrices(self, prover_data: MerkleTree):
+        return list(prover_data.leaves)
+
+    def get_max_height(self, prover_data: MerkleTree):
+        return max(int(m.shape[0]) for m in prover_data.leaves)
+
+    # merkle-tree/src/mmcs/batch.rs:75-121
+    def open_batch(self, index: int, prover_data: MerkleTree):
+        max_height = self.get_max_height(prover_data)
+        if index >= max_height:
+            raise IndexError(f"index {index} out of bounds for height {max_height}")
+        log_max = _log2_ceil(max_height)
+        openings = []
+        for m in prover_data.leaves:
+            bits_reduced = log_max - _log2_ceil(int(m.shape[0]))
+            openings.append(_host(m[index >> bits_reduced]))
+        nl = prover_data.num_layers()
+        eff = min(self.cap_height, max(nl - 1, 0))
+        proof, idx = [], index
+        for layer_idx in range(nl - 1 - eff):
+            proof.append(_host(prover_data.digest_layers[layer_idx][(idx ^ 1):(idx ^ 1) + 1])[0])
+            idx >>= 1
+        return openings, proof

@@ -1,0 +1,70 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads and exports every symbol include/p3gpu.h declares,
+host logic (arity schedule, field helpers, height ladder) matches the reference's definitions, and the product path
+fails loudly without a CUDA device.  No compute calls here."""
+import pathlib
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import plonky3_b200 as P
+from plonky3_b200 import _lib
+from plonky3_b200.field import BabyBear, KoalaBear
+from plonky3_b200.fri import compute_log_arity_for_round, FriParameters
+
+ROOT = pathlib.Path(__file__).resolve().parent.parent
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = (ROOT / "include" / "p3gpu.h").read_text()
+    declared = sorted(set(re.findall(r"\b(p3gpu_[a-z0-9_]+)\s*\(", hdr)))
+    assert declared, "no declarations found"
+    L = _lib.load()
+    missing = [n for n in declared if not hasattr(L, n)]
+    assert not missing, missing
+    assert sorted(_lib.EXPORTS) == declared
+
+
+def test_no_cpu_fallback():
+    if torch.cuda.is_available():
+        pytest.skip("device present")
+    from plonky3_b200.gpu import Gpu
+    with pytest.raises(P.P3GpuError, match="no CPU fallback"):
+        Gpu(0)
+
+
+def test_product_never_imports_oracle():
+    """The oracle is test infrastructure: nothing under plonky3_b200/ may import, link or load it."""
+    pat = re.compile(r"p3_oracle|libp3oracle|^\s*(from|import)\s+oracle|oracle/", re.M)
+    for f in (ROOT / "plonky3_b200").rglob("*"):
+        if f.suffix in (".py", ".cu", ".cuh", ".h", ".sh"):
+            assert not pat.search(f.read_text()), f
+
+
+def test_field_helpers_match_reference_constants():
+    # SURVEY Appendix A (baby_bear.rs:17-68, koala_bear.rs:20-94)
+    assert BabyBear.ONE == 0x0FFFFFFE and KoalaBear.ONE == 0x01FFFFFE
+    assert BabyBear.from_monty(BabyBear.two_adic_generator(27)) == 0x1A427A41
+    assert KoalaBear.from_monty(KoalaBear.two_adic_generator(24)) == 0x6AC49F88
+    assert KoalaBear.from_monty(KoalaBear.two_adic_generator(1)) == KoalaBear.P - 1
+    a = np.array([0, 1, 5, KoalaBear.P - 1], dtype=np.uint32)
+    assert np.array_equal(KoalaBear.from_monty_array(KoalaBear.to_monty_array(a)), a)
+    with pytest.raises(ValueError):
+        KoalaBear.two_adic_generator(25)
+
+
+def test_arity_schedule():
+    # fri/src/config.rs:180-207 and SURVEY §8 a17: cfg5 2^21 -> [3,3,3,3,3,3,2], cfg4 2^23 -> [3]*7+[1]
+    def sched(log_len, log_final, mx):
+        out = []
+        while log_len > log_final:
+            a = compute_log_arity_for_round(log_len, None, log_final, mx); out.append(a); log_len -= a
+        return out
+    assert sched(21, 1, 3) == [3, 3, 3, 3, 3, 3, 2]
+    assert sched(23, 1, 3) == [3] * 7 + [1]
+    assert compute_log_arity_for_round(10, 8, 1, 3) == 2
+    with pytest.raises(ValueError):
+        compute_log_arity_for_round(5, None, 1, 0)
+    p = FriParameters.new_benchmark_high_arity(None)
+    assert (p.log_blowup, p.max_log_arity, p.num_queries, p.query_proof_of_work_bits) == (1, 3, 100, 16)

@@ -1,0 +1,325 @@
+"""GPU parity tests: every hot-path entry point of libp3gpu (called through the C ABI via plonky3_b200) against the CPU
+oracle on the same seeded inputs — bit-exact — plus size-independent properties at the BASELINE.json sizes.
+Run on the B200 box with `pytest -m gpu`."""
+import json
+import pathlib
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import p3_oracle as O
+import fixture_replay as FR
+
+import plonky3_b200 as P
+from plonky3_b200 import _lib
+from plonky3_b200.dft import Radix2DitParallel, reverse_matrix_index_bits
+from plonky3_b200.field import BabyBear, KoalaBear
+from plonky3_b200.fri import FriParameters, TwoAdicFriFolding, TwoAdicFriPcs, commit_phase
+from plonky3_b200.gpu import default_gpu
+from plonky3_b200.merkle_tree import MerkleTreeMmcs
+from plonky3_b200.poseidon2 import Poseidon2, default_poseidon2
+
+pytestmark = pytest.mark.gpu
+GOLD = pathlib.Path(__file__).resolve().parent / "golden"
+FIELDS = [BabyBear, KoalaBear]
+
+
+@pytest.fixture(scope="module")
+def gpu():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    assert _lib.LIB_PATH.exists(), "libp3gpu.so missing — the CUDA path must be the one that runs"
+    return default_gpu(0)
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.uint32).view(np.int32)).cuda()
+
+
+def host(t):
+    return t.cpu().numpy().view(np.uint32)
+
+
+# ------------------------------------------------------------------------------------------ config 1
+def test_config1_forward_ntt_babybear_2_16(gpu):
+    """BASELINE config 1: Radix2DitParallel forward NTT, BabyBear, 2^16 x 1, bit-exact; plus the edge inputs."""
+    f = BabyBear
+    dft = Radix2DitParallel(f, gpu)
+    h = 1 << 16
+    m = O.random_matrix(f.id, h, 1, seed=1)
+    assert np.array_equal(dft.dft_batch(m), O.dft_batch(f.id, m))
+    assert np.array_equal(dft.dft(m.ravel()), O.dft_batch(f.id, m).ravel())
+    zero = np.zeros((h, 1), dtype=np.uint32)
+    assert not dft.dft_batch(zero).any()
+    delta = zero.copy(); delta[0, 0] = f.ONE
+    assert (dft.dft_batch(delta) == f.ONE).all()
+    allm1 = np.full((h, 1), f.to_monty(f.P - 1), dtype=np.uint32)
+    assert np.array_equal(dft.dft_batch(allm1), O.dft_batch(f.id, allm1))
+
+
+@pytest.mark.parametrize("f", FIELDS, ids=lambda f: f.name)
+@pytest.mark.parametrize("log_h,w", [(0, 3), (1, 1), (2, 5), (3, 17), (5, 4), (7, 33), (9, 100), (10, 7), (11, 36), (12, 3), (13, 20), (15, 2)])
+def test_dft_family_matches_oracle(gpu, f, log_h, w):
+    # dft/tests/testing.rs:298-378: dft / idft / coset_dft / coset_idft agree with the definition for many shapes
+    dft = Radix2DitParallel(f, gpu)
+    m = O.random_matrix(f.id, 1 << log_h, w, seed=100 * log_h + w)
+    shift = f.to_monty(0x2345678 + log_h)
+    assert np.array_equal(dft.dft_batch(m), O.dft_batch(f.id, m))
+    assert np.array_equal(dft.idft_batch(m), O.idft_batch(f.id, m))
+    assert np.array_equal(dft.coset_dft_batch(m, shift), O.coset_dft_batch(f.id, m, shift))
+    assert np.array_equal(dft.coset_idft_batch(m, shift), O.coset_idft_batch(f.id, m, shift))
+    # device-resident path gives the same answer as the host-pointer path
+    assert np.array_equal(host(dft.dft_batch(dev(m))), O.dft_batch(f.id, m))
+
+
+@pytest.mark.parametrize("f", FIELDS, ids=lambda f: f.name)
+def test_small_dft_vs_naive_definition(gpu, f):
+    # field-testing/src/dft_testing.rs:307-405 (h <= 16, w = 3 vs NaiveDft)
+    dft = Radix2DitParallel(f, gpu)
+    for log_h in range(0, 5):
+        m = O.random_matrix(f.id, 1 << log_h, 3, seed=log_h)
+        assert np.array_equal(dft.dft_batch(m), O.naive_dft(f.id, m))
+
+
+@pytest.mark.parametrize("f", FIELDS, ids=lambda f: f.name)
+@pytest.mark.parametrize("log_h,w,added_bits", [(0, 2, 1), (1, 3, 2), (4, 5, 0), (4, 5, 1), (6, 9, 3), (10, 100, 1), (12, 37, 1), (13, 8, 2), (14, 4, 1)])
+def test_coset_lde_matches_oracle(gpu, f, log_h, w, added_bits):
+    # traits.rs:227-259 + radix_2_dit_parallel.rs:181-246: values AND memory layout (bit-reversed rows)
+    dft = Radix2DitParallel(f, gpu)
+    m = O.random_matrix(f.id, 1 << log_h, w, seed=7 * log_h + w)
+    shift = f.generator
+    view = dft.coset_lde_batch(m, added_bits, shift)
+    assert np.array_equal(view.bit_reverse_rows(), O.coset_lde_batch(f.id, m, added_bits, shift, bitrev_out=True))
+    assert np.array_equal(view.to_row_major_matrix(), O.coset_lde_batch(f.id, m, added_bits, shift, bitrev_out=False))
+    nat = gpu.coset_lde_batch(f.id, m, added_bits, shift, bitrev_rows=False)
+    assert np.array_equal(nat, O.coset_lde_batch(f.id, m, added_bits, shift, bitrev_out=False))
+    assert np.array_equal(host(dft.coset_lde_batch(dev(m), added_bits, shift).bit_reverse_rows()), view.bit_reverse_rows())
+    assert np.array_equal(dft.lde_batch(m, added_bits).bit_reverse_rows(), O.coset_lde_batch(f.id, m, added_bits, f.ONE, True))
+
+
+def test_dft_shape_errors(gpu):
+    # the reference panics in log2_strict_usize on non power-of-two heights; the C ABI returns P3GPU_EINVAL
+    with pytest.raises(P.P3GpuError, match="power of two"):
+        gpu.dft_batch(0, _lib.DFT, np.zeros((6, 2), dtype=np.uint32))
+    # 2^24 rows + 1 added bit exceeds KoalaBear's two-adicity (24): rejected before any memory is touched
+    rc = gpu.L.p3gpu_coset_lde_batch_dev(gpu.h, KoalaBear.id, 256, 1 << 24, 1, 1, KoalaBear.ONE, 512, 1)
+    assert rc == -1 and b"two-adicity" in gpu.L.p3gpu_last_error()
+    with pytest.raises(ValueError):
+        Radix2DitParallel(KoalaBear, gpu).dft_batch(np.zeros((12, 1), dtype=np.uint32))
+
+
+# ------------------------------------------------------------------------------------------ hashing
+def test_poseidon2_kats_on_gpu(gpu):
+    # koala-bear/src/poseidon2.rs:614-653, baby-bear/src/poseidon2.rs:599-639
+    kats = json.loads((GOLD / "poseidon2_kat.json").read_text())
+    for f in FIELDS:
+        for w in (16, 24):
+            k = kats[f"{f.name}_{w}"]
+            pm = default_poseidon2(f, w)
+            out = pm.permute(gpu, f.to_monty_array(k["input"]).reshape(1, w))
+            assert f.from_monty_array(out[0]).tolist() == k["expected"]
+
+
+@pytest.mark.parametrize("f", FIELDS, ids=lambda f: f.name)
+@pytest.mark.parametrize("w", [16, 24])
+def test_poseidon2_random_states(gpu, f, w):
+    pm = default_poseidon2(f, w)
+    st = O.random_matrix(f.id, 300, w, seed=w)
+    st[0] = 0; st[1] = f.P - 1
+    out = pm.permute(gpu, st)
+    opm = O.default_perm(f.id, w)
+    for i in range(0, 300, 7):
+        assert np.array_equal(out[i], O.poseidon2_permute(opm, st[i]))
+
+
+def test_keccak_f_on_gpu(gpu):
+    rng = np.random.default_rng(3)
+    st = rng.integers(0, 1 << 63, size=(70, 25), dtype=np.uint64) * 2 + rng.integers(0, 2, size=(70, 25), dtype=np.uint64)
+    st[0] = 0
+    out = gpu.keccak_f(st)
+    for i in range(70):
+        assert np.array_equal(out[i], O.keccak_f(st[i]))
+
+
+def _mmcs_pair(f, kind, gpu, cap_height=0):
+    """(GPU mmcs, oracle hasher) for one of the three hash configurations."""
+    if kind == "keccak":
+        return MerkleTreeMmcs.keccak(f, cap_height, gpu), O.keccak_hasher()
+    p16 = default_poseidon2(f, 16)
+    if kind == "p2w16":
+        return MerkleTreeMmcs.poseidon2(p16, None, cap_height, gpu), O.poseidon2_hasher(O.default_perm(f.id, 16), O.default_perm(f.id, 16))
+    return MerkleTreeMmcs.poseidon2(p16, default_poseidon2(f, 24), cap_height, gpu), O.poseidon2_hasher(O.default_perm(f.id, 24), O.default_perm(f.id, 16))
+
+
+def _check_tree(tree, olayers):
+    assert len(tree.digest_layers) == len(olayers)
+    for a, b in zip(tree.digest_layers, olayers):
+        a = host(a) if torch.is_tensor(a) else a
+        assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("kind", ["p2w16", "p2w24", "keccak"])
+@pytest.mark.parametrize("f", FIELDS, ids=lambda f: f.name)
+def test_merkle_single_matrix_widths(gpu, f, kind):
+    # widths below / equal / above the sponge rate, odd widths (Keccak pair packing), wide rows
+    mmcs, ohs = _mmcs_pair(f, kind, gpu)
+    for h, w in [(1, 5), (2, 8), (8, 1), (16, 16), (32, 17), (64, 33), (128, 34), (256, 35), (512, 100), (1024, 7)]:
+        m = O.random_matrix(f.id, h, w, seed=h + w)
+        cap, tree = mmcs.commit([m])
+        ol = O.merkle_tree(ohs, [m])
+        _check_tree(tree, ol)
+        assert np.array_equal(cap, O.merkle_cap(ol, 0))
+        cap_d, tree_d = mmcs.commit([dev(m)])
+        _check_tree(tree_d, ol)
+
+
+@pytest.mark.parametrize("kind", ["p2w16", "p2w24", "keccak"])
+def test_merkle_mixed_heights_caps_and_padding(gpu, kind):
+    f = KoalaBear
+    mmcs, ohs = _mmcs_pair(f, kind, gpu, cap_height=2)
+    mats = [O.random_matrix(f.id, 64, 3, seed=1), O.random_matrix(f.id, 256, 9, seed=2), O.random_matrix(f.id, 256, 5, seed=3),
+            O.random_matrix(f.id, 8, 21, seed=4), O.random_matrix(f.id, 64, 2, seed=5)]
+    cap, tree = mmcs.commit(mats)
+    ol = O.merkle_tree(ohs, mats)
+    _check_tree(tree, ol)
+    assert np.array_equal(cap, O.merkle_cap(ol, 2)) and cap.shape == (4, 8)
+    # non power-of-two heights on the ladder: 21 -> 11 -> 6 (merkle_tree.rs:652-711 padding with the zero digest)
+    mats = [O.random_matrix(f.id, 21, 4, seed=6), O.random_matrix(f.id, 11, 3, seed=7), O.random_matrix(f.id, 6, 2, seed=8)]
+    cap, tree = mmcs.commit(mats)
+    _check_tree(tree, O.merkle_tree(ohs, mats))
+    # open_batch: rows and sibling path (mmcs/batch.rs:75-121)
+    openings, proof = mmcs.open_batch(13, tree)
+    assert np.array_equal(openings[0], mats[0][13]) and np.array_equal(openings[1], mats[1][6]) and np.array_equal(openings[2], mats[2][3])
+    # heights off the ladder are rejected (mmcs/geometry.rs:83-124)
+    with pytest.raises(P.P3GpuError, match="incompatible"):
+        mmcs.commit([O.random_matrix(f.id, 8, 1), O.random_matrix(f.id, 3, 1)])
+    with pytest.raises(P.P3GpuError):
+        mmcs.commit([])
+
+
+# ------------------------------------------------------------------------------------------ FRI
+@pytest.mark.parametrize("f", FIELDS, ids=lambda f: f.name)
+@pytest.mark.parametrize("log_arity", [1, 2, 3, 4])
+def test_fold_matrix_matches_oracle(gpu, f, log_arity):
+    fold = TwoAdicFriFolding(f, gpu)
+    for log_len in (log_arity, log_arity + 1, 9, 13):
+        v = O.random_matrix(f.id, 1 << log_len, 4, seed=log_len)
+        beta = O.random_matrix(f.id, 1, 4, seed=99)[0]
+        exp = O.fold_matrix(f.id, v, log_arity, beta)
+        assert np.array_equal(fold.fold_matrix(beta, log_arity, v), exp)
+        assert np.array_equal(host(fold.fold_matrix(beta, log_arity, dev(v))), exp)
+
+
+class FixedBetaChallenger:
+    """Transcript stand-in for parity tests: records caps, returns a fixed beta list (PoW bits = 0)."""
+
+    def __init__(self, betas): self.betas = list(betas); self.caps = []; self.final = None
+    def observe_cap(self, cap): self.caps.append(np.array(cap))
+    def grind(self, bits): assert bits == 0; return 0
+    def sample_algebra_element(self): return self.betas.pop(0)
+    def observe_algebra_slice(self, v): self.final = np.array(v)
+
+
+@pytest.mark.parametrize("kind,f", [("p2w16", BabyBear), ("p2w24", KoalaBear), ("keccak", BabyBear)])
+def test_commit_phase_matches_oracle(gpu, kind, f):
+    # fri/src/prover.rs:192-286 with benchmark parameters (blowup 2, max arity 8, no commit PoW), cap_height 3
+    mmcs, ohs = _mmcs_pair(f, kind, gpu, cap_height=3)
+    params = FriParameters.new_benchmark_high_arity(mmcs)
+    log_len = 12
+    vec = O.random_matrix(f.id, 1 << log_len, 4, seed=5)
+    betas = O.random_matrix(f.id, 8, 4, seed=6)
+    ocaps, oar, ofinal = O.commit_phase(f.id, ohs, 3, vec, params.log_blowup, params.log_final_poly_len, params.max_log_arity, betas)
+    ch = FixedBetaChallenger(betas)
+    res = commit_phase(TwoAdicFriFolding(f, gpu), params, [dev(vec)], ch, Radix2DitParallel(f, gpu))
+    assert res.log_arities == oar == [3, 3, 3, 2]
+    for a, b in zip(res.commits, ocaps):
+        assert np.array_equal(a, b)
+    assert np.array_equal(res.final_poly, ofinal[:1])
+    # single-call device driver
+    caps, las, final = gpu.fri_commit_phase(f.id, mmcs.hash_kind, dev(vec), 1, 0, 3, 3, betas)
+    assert las == oar and all(np.array_equal(a, b) for a, b in zip(caps, ocaps)) and np.array_equal(final, ofinal)
+
+
+def test_pcs_commit_matches_oracle(gpu):
+    # TwoAdicFriPcs::commit (two_adic_pcs.rs:300-324): LDE onto GENERATOR*K, bit-reversed, Poseidon2 MMCS
+    f = KoalaBear
+    mmcs, ohs = _mmcs_pair(f, "p2w24", gpu, cap_height=3)
+    pcs = TwoAdicFriPcs(Radix2DitParallel(f, gpu), mmcs, FriParameters.new_benchmark_high_arity(mmcs))
+    m = O.random_matrix(f.id, 1 << 10, 45, seed=8)
+    cap, tree = pcs.commit([(pcs.natural_domain_for_degree(1 << 10), m)])
+    lde = O.coset_lde_batch(f.id, m, 1, f.generator, bitrev_out=True)
+    ol = O.merkle_tree(ohs, [lde])
+    assert np.array_equal(cap, O.merkle_cap(ol, 3))
+    assert np.array_equal(mmcs.get_matrices(tree)[0], lde)
+    lde_d, layers = gpu.pcs_commit(f.id, mmcs.hash_kind, dev(m), 1)
+    assert np.array_equal(host(lde_d), lde) and np.array_equal(host(layers[-1]), ol[-1])
+    ev = pcs.get_evaluations_on_domain(tree, 0, (f.generator, 10))
+    assert np.array_equal(ev.to_row_major_matrix(), O.coset_dft_batch(f.id, O.idft_batch(f.id, m), f.generator))
+
+
+class GpuBackend:
+    """fixture_replay backend on the GPU: every hot-path step of the proof goes through libp3gpu."""
+
+    def __init__(self, gpu):
+        rc_i, rc_t, rc_p = FR.fixture_constants()
+        pm = Poseidon2.new(BabyBear, 16, rc_i, rc_t, rc_p, monty=True)
+        self.mmcs = MerkleTreeMmcs.poseidon2(pm, None, 0, gpu)
+        self.dft = Radix2DitParallel(BabyBear, gpu)
+        self.folding = TwoAdicFriFolding(BabyBear, gpu)
+
+    def lde(self, mat, added_bits, shift): return self.dft.coset_lde_batch(mat, added_bits, shift).bit_reverse_rows()
+    def commit(self, mats): return self.mmcs.commit(mats)[0]
+    def fold(self, vec, log_arity, beta): return self.folding.fold_matrix(beta, log_arity, vec)
+
+
+def test_fixture_replay_on_gpu(gpu):
+    """The reference's committed proof (uni_stark_two_adic_v1.postcard) is reproduced with LDE, Merkle and FRI fold on the GPU."""
+    gold = json.loads((GOLD / "uni_stark_two_adic_v1.json").read_text())
+    got = FR.replay(GpuBackend(gpu))
+    for k, v in got.items():
+        assert v == gold[k], k
+
+
+# ------------------------------------------------------------------------------------------ full-size properties
+def test_config2_lde_full_size_properties(gpu):
+    """BASELINE config 2 (KoalaBear 2^20 x 100, blowup 2): spot columns vs the oracle + round trip + linearity."""
+    f = KoalaBear
+    h, w = 1 << 20, 100
+    dft = Radix2DitParallel(f, gpu)
+    g = torch.Generator(device="cuda"); g.manual_seed(1)
+    x = torch.randint(0, f.P, (h, w), device="cuda", dtype=torch.int32, generator=g)
+    lde = dft.coset_lde_batch(x, 1, f.generator).bit_reverse_rows()
+    cols = [0, 37, 99]
+    xs = host(x[:, cols].contiguous())
+    exp = O.coset_lde_batch(f.id, xs, 1, f.generator, bitrev_out=True)
+    assert np.array_equal(host(lde[:, cols].contiguous()), exp)
+    # round trip: the first h memory rows are the evaluations on GENERATOR*H (bit-reversed) -> coset iDFT gives idft(x)
+    first = reverse_matrix_index_bits(lde[:h].contiguous())
+    assert torch.equal(dft.coset_idft_batch(first, f.generator), dft.idft_batch(x))
+    # linearity: LDE(x + y) = LDE(x) + LDE(y)
+    y = torch.randint(0, f.P, (h, w), device="cuda", dtype=torch.int32, generator=g)
+    s = (x.long() + y.long()) % f.P
+    lde_y = dft.coset_lde_batch(y, 1, f.generator).bit_reverse_rows()
+    lde_s = dft.coset_lde_batch(s.int(), 1, f.generator).bit_reverse_rows()
+    assert torch.equal(lde_s.long(), (lde.long() + lde_y.long()) % f.P)
+
+
+def test_config3_merkle_full_size_properties(gpu):
+    """BASELINE config 3 (KoalaBear 2^22 x 100, Poseidon2-16 sponge): sub-tree consistency + spot leaves vs oracle."""
+    f = KoalaBear
+    h, w = 1 << 22, 100
+    mmcs, ohs = _mmcs_pair(f, "p2w16", gpu)
+    g = torch.Generator(device="cuda"); g.manual_seed(1)
+    x = torch.randint(0, f.P, (h, w), device="cuda", dtype=torch.int32, generator=g)
+    cap, tree = mmcs.commit([x])
+    assert [int(l.shape[0]) for l in tree.digest_layers] == [h >> k for k in range(23)]
+    for r in (0, 1, 12345, h - 1):
+        assert np.array_equal(host(tree.digest_layers[0][r:r + 1])[0], O.hash_row(ohs, host(x[r:r + 1])[0]))
+    # the tree over the first 2^12 rows is the left-most sub-tree: its root is node 0 of layer 12
+    sub = O.merkle_tree(ohs, [host(x[: 1 << 12].contiguous())])
+    assert np.array_equal(sub[-1][0], host(tree.digest_layers[12][0:1])[0])
+    # a checksum of checksums: root recomputed from layer 12 on the CPU
+    lay = host(tree.digest_layers[12].contiguous())
+    while lay.shape[0] > 1:
+        lay = np.array([O.compress(ohs, lay[2 * i], lay[2 * i + 1]) for i in range(lay.shape[0] // 2)])
+    assert np.array_equal(lay[0], cap[0])
