@@ -62,8 +62,10 @@ enum {
 /* ---- context ---------------------------------------------------------------------------------- */
 int32_t p3gpu_ctx_create(int device, p3gpu_ctx **out);
 void p3gpu_ctx_destroy(p3gpu_ctx *ctx);
-/* run subsequent _dev calls on this cudaStream_t (e.g. torch's current stream); NULL = the context's own stream */
+/* run subsequent calls on this cudaStream_t (e.g. torch's current stream); NULL = the legacy default stream.
+ * A fresh context uses a private non-blocking stream; p3gpu_ctx_use_own_stream switches back to it. */
 int32_t p3gpu_ctx_set_stream(p3gpu_ctx *ctx, void *cuda_stream);
+int32_t p3gpu_ctx_use_own_stream(p3gpu_ctx *ctx);
 int32_t p3gpu_ctx_sync(p3gpu_ctx *ctx);
 const char *p3gpu_last_error(void);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */

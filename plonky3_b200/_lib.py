@@ -13,7 +13,7 @@ DFT, IDFT, COSET_DFT, COSET_IDFT = 0, 1, 2, 3
 HASH_POSEIDON2_W16, HASH_POSEIDON2_W24, HASH_KECCAK = 0, 1, 2
 
 EXPORTS = [
-    "p3gpu_ctx_create", "p3gpu_ctx_destroy", "p3gpu_ctx_set_stream", "p3gpu_ctx_sync", "p3gpu_last_error",
+    "p3gpu_ctx_create", "p3gpu_ctx_destroy", "p3gpu_ctx_set_stream", "p3gpu_ctx_use_own_stream", "p3gpu_ctx_sync", "p3gpu_last_error",
     "p3gpu_launch_count", "p3gpu_malloc", "p3gpu_free", "p3gpu_memcpy_h2d", "p3gpu_memcpy_d2h",
     "p3gpu_host_register", "p3gpu_host_unregister",
     "p3gpu_dft_batch_dev", "p3gpu_dft_batch", "p3gpu_coset_lde_batch_dev", "p3gpu_coset_lde_batch",
@@ -43,6 +43,7 @@ def load():
         "p3gpu_ctx_create": (i32, [ci, C.POINTER(vp)]),
         "p3gpu_ctx_destroy": (None, [vp]),
         "p3gpu_ctx_set_stream": (i32, [vp, vp]),
+        "p3gpu_ctx_use_own_stream": (i32, [vp]),
         "p3gpu_ctx_sync": (i32, [vp]),
         "p3gpu_last_error": (C.c_char_p, []),
         "p3gpu_launch_count": (C.c_uint64, [vp]),

@@ -89,7 +89,12 @@ void p3gpu_ctx_destroy(p3gpu_ctx *ctx) {
 
 int32_t p3gpu_ctx_set_stream(p3gpu_ctx *ctx, void *cuda_stream) {
     P3_CHECK(ctx, P3GPU_EINVAL, "null context");
-    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    ctx->stream = (cudaStream_t)cuda_stream;  // NULL is the legacy default stream (what torch uses by default)
+    return P3GPU_OK;
+}
+int32_t p3gpu_ctx_use_own_stream(p3gpu_ctx *ctx) {
+    P3_CHECK(ctx, P3GPU_EINVAL, "null context");
+    ctx->stream = ctx->own_stream;
     return P3GPU_OK;
 }
 int32_t p3gpu_ctx_sync(p3gpu_ctx *ctx) {
