@@ -1,0 +1,275 @@
+#!/usr/bin/env python3
+"""bench.py — the driver's benchmark contract for the Plonky3 hot path on B200.
+
+Default workload (N=1) = BASELINE.json configs[1]: coset_lde_batch, KoalaBear, 2^20 rows x 100 cols, blowup 2
+(added_bits = 1, shift = GENERATOR), output in the committed (bit-reversed-row) layout.  metric = NTT Gelem/s of LDE
+output.  A "step" is one LDE of one synthetic matrix (uniform field elements, seed 1).
+
+  value       device-resident throughput: input already in HBM, CUDA events on the launching stream, K steps.
+              Input (419 MB) + output (839 MB) exceed the 126 MB L2, so no L2 flush is needed between iterations.
+  e2e         the same metric through the reference-facing C-ABI call p3gpu_coset_lde_batch with HOST (pinned) buffers:
+              H2D of the input and D2H of the result are inside the timed region.
+  roofline    HBM roofline of the NTT pass kernel: algorithmic bytes of one LDE (read input once + write output once,
+              SURVEY.md §8d: 1,258,291,200 B) / device time of the step (all launches of a step are the same kernel).
+  cpu_baseline the oracle port (OpenMP C restatement, oracle/p3_oracle.c) on the host cores, bounded sample.
+  others      (N=1 only) the remaining single-GPU BASELINE configs timed the same way (Merkle config 3, Keccak commit
+              config 4 shape scaled to fit the time budget is reported at its own size, FRI commit phase).
+
+--impl reference: times the reference's CPU algorithm (the oracle port — the reference is Rust and cannot be built in this
+image) on the same metric; rank 0 only under torchrun.
+Multi-GPU (--gpus N under torchrun): the path shards by independent matrices/column blocks with no data-path collective
+(SURVEY.md §8e); every rank runs the same per-GPU workload (weak scaling), timing = max over ranks.
+"""
+import argparse
+import json
+import os
+import pathlib
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = pathlib.Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+LOG_H, W, ADDED_BITS = 20, 100, 1
+ALG_BYTES = ((1 << LOG_H) * W + (1 << (LOG_H + ADDED_BITS)) * W) * 4       # 1,258,291,200
+OUT_ELEMS = (1 << (LOG_H + ADDED_BITS)) * W                                   # 209,715,200
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-others", action="store_true", help="skip the secondary workloads")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    def __init__(self, idx=0):
+        self.idx, self.samples, self.reasons, self.stop = idx, [], set(), False
+        self.max_mhz = None
+        self.t = threading.Thread(target=self.run, daemon=True)
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self.stop:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                self.samples.append(float(out[0])); self.max_mhz = float(out[1])
+                for n, v in zip(names, out[2:]):
+                    if v.strip().lower() == "active":
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def __enter__(self): self.t.start(); return self
+    def __exit__(self, *a): self.stop = True; self.t.join(timeout=6)
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU (oracle) legs
+def cpu_lde_throughput(budget_s=15.0):
+    """Oracle port of coset_lde_batch on a bounded column sample of the same workload.  Returns (Gelem/s, cores, sample)."""
+    from oracle import p3_oracle as O
+    O.build(native=True)          # rebuild with -march=native for THIS host
+    cores = os.cpu_count() or 1
+    f = 1
+    m = O.random_matrix(f, 1 << LOG_H, 4, seed=1)
+    t0 = time.time(); O.coset_lde_batch(f, m, ADDED_BITS, O.generator(f)); t4 = time.time() - t0
+    cols = int(max(4, min(W, 4 * budget_s / max(t4, 1e-3))))
+    cols -= cols % 4
+    m = O.random_matrix(f, 1 << LOG_H, cols, seed=1)
+    t0 = time.time(); out = O.coset_lde_batch(f, m, ADDED_BITS, O.generator(f)); dt = time.time() - t0
+    return out.size / dt / 1e9, cores, f"coset_lde_batch KoalaBear 2^{LOG_H} x {cols} of {W} cols, blowup 2, {dt:.1f} s, OpenMP {cores} threads"
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import p3_oracle as O
+    O.build(native=True)
+    cores = os.cpu_count() or 1
+    f = 1
+    cols = 8
+    m = O.random_matrix(f, 1 << LOG_H, cols, seed=1)
+    for _ in range(min(args.warmup, 1)):
+        O.coset_lde_batch(f, m, ADDED_BITS, O.generator(f))
+    steps = max(1, min(args.steps, 5))
+    t0 = time.time()
+    for _ in range(steps):
+        out = O.coset_lde_batch(f, m, ADDED_BITS, O.generator(f))
+    dt = (time.time() - t0) / steps
+    v = out.size / dt / 1e9
+    sample = f"coset_lde_batch KoalaBear 2^{LOG_H} x {cols} of {W} cols per step (bounded sample), OpenMP {cores} threads"
+    print(json.dumps({
+        "impl": "reference", "metric": "coset_lde_batch output Gelem/s (KoalaBear 2^20 x 100, blowup 2)", "value": v, "unit": "Gelem/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3 * (W / cols),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 (31-bit Montgomery)", "data": "synthetic",
+        "config": {"workload": "coset_lde_batch KoalaBear 2^20 x 100, added_bits 1, shift GENERATOR (BASELINE configs[1])"},
+        "cpu_baseline": {"value": v, "unit": "Gelem/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "Gelem/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "reference is Rust (no toolchain in this image): this is the OpenMP C restatement oracle/p3_oracle.c; ms_per_step is scaled to 100 columns",
+    }))
+
+
+# ------------------------------------------------------------------------------------------------ GPU legs
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from plonky3_b200 import _lib
+    from plonky3_b200.field import KoalaBear as KB, BabyBear as BB
+    from plonky3_b200.gpu import Gpu
+    from plonky3_b200.poseidon2 import default_poseidon2
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    gpu = Gpu(local)
+    for f in (KB, BB):
+        for w in (16, 24):
+            default_poseidon2(f, w).upload(gpu)
+    dev = f"cuda:{local}"
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        """W warm-up steps, then K timed steps bracketed by barrier+synchronize, CUDA events, max over ranks."""
+        for _ in range(warmup):
+            fn()
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = gpu.launches
+        a.record()
+        for _ in range(steps):
+            fn()
+        b.record()
+        barrier()
+        ms = a.elapsed_time(b)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms / steps, (gpu.launches - l0)
+
+    # ---- primary: coset LDE, device resident (weak scaling: one matrix per rank)
+    g = torch.Generator(device=dev); g.manual_seed(1 + rank)
+    x = torch.randint(0, KB.P, (1 << LOG_H, W), device=dev, dtype=torch.int32, generator=g)
+    out = torch.empty((1 << (LOG_H + ADDED_BITS), W), device=dev, dtype=torch.int32)
+    gpu._use_torch_stream()
+
+    def lde_step():
+        _lib.check(gpu.L.p3gpu_coset_lde_batch_dev(gpu.h, KB.id, x.data_ptr(), 1 << LOG_H, W, ADDED_BITS, KB.generator, out.data_ptr(), 1))
+
+    with ClockSampler(local) as clk:
+        ms, launches = timed(lde_step, args.steps, max(args.warmup, 3))
+    value = world * OUT_ELEMS / (ms * 1e-3) / 1e9
+
+    # ---- e2e: host-pointer C-ABI call, pinned host buffers, copies inside the timed region
+    hx = torch.empty((1 << LOG_H, W), dtype=torch.int32).pin_memory(); hx.copy_(x.cpu())
+    hout = torch.empty((1 << (LOG_H + ADDED_BITS), W), dtype=torch.int32).pin_memory()
+
+    def e2e_step():
+        _lib.check(gpu.L.p3gpu_coset_lde_batch(gpu.h, KB.id, hx.data_ptr(), 1 << LOG_H, W, ADDED_BITS, KB.generator, hout.data_ptr(), 1))
+
+    e2e_steps = max(3, min(args.steps, 5))
+    e2e_ms, _ = timed(e2e_step, e2e_steps, 1)
+    assert torch.equal(hout.to(dev), out), "e2e result differs from device-resident result"
+    e2e = {"value": world * OUT_ELEMS / (e2e_ms * 1e-3) / 1e9, "unit": "Gelem/s", "ms_per_step": e2e_ms,
+           "h2d_bytes_per_step": hx.numel() * 4, "d2h_bytes_per_step": hout.numel() * 4,
+           "api": "p3gpu_coset_lde_batch (host pointers, pinned)"}
+
+    line = {
+        "metric": "coset_lde_batch output Gelem/s (KoalaBear 2^20 x 100, blowup 2)", "value": value, "unit": "Gelem/s",
+        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u32 (31-bit Montgomery)", "data": "synthetic",
+        "config": {"workload": "coset_lde_batch KoalaBear 2^20 x 100, added_bits 1, shift GENERATOR, bit-reversed rows (BASELINE configs[1])",
+                   "per_gpu_matrices": 1, "l2_policy": "inputs+outputs (1.26 GB) exceed the 126 MB L2; no flush needed"},
+        "e2e": e2e, "gpu_launches": launches, "clocks": clk.summary(),
+    }
+
+    # ---- roofline of the dominant kernel (ntt_pass_kernel): every launch of the step is this kernel
+    peaks_path = ROOT / "MEASURED_PEAKS.json"
+    if peaks_path.exists():
+        peak, peak_src = json.loads(peaks_path.read_text())["hbm_gbs"], "MEASURED_PEAKS.json hbm_gbs (of measured)"
+    else:
+        peak, peak_src = 6650.0, "B200_PROFILING.md fallback (of fallback)"
+    achieved = ALG_BYTES / (ms * 1e-3) / 1e9
+    traffic = None
+    tp = ROOT / "profiles" / "ncu_traffic.json"
+    if tp.exists():
+        traffic = json.loads(tp.read_text()).get("lde_step_dram_bytes")
+    line["roofline"] = {"bound": "hbm", "kernel": "ntt_pass_kernel (all launches of an LDE step)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                        "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                        "algorithmic_bytes_per_step": ALG_BYTES, "launches_per_step": launches / args.steps,
+                        "note": "kernel is integer-issue bound (3 IMAD + 6 ALU per butterfly, 3.146e9 butterflies): see DESIGN.md"}
+
+    # ---- secondary workloads (single GPU only)
+    if world == 1 and not args.no_others:
+        others = {}
+        k = max(2, min(args.steps, 5))
+        # config 3: MerkleTreeMmcs commit 2^22 x 100 KoalaBear, Poseidon2-16 sponge, cap 0
+        xm = torch.randint(0, KB.P, (1 << 22, 100), device=dev, dtype=torch.int32, generator=g)
+        t, nl = timed(lambda: gpu.merkle_commit(KB.id, _lib.HASH_POSEIDON2_W16, [xm]), k, 1)
+        others["merkle_commit_poseidon2_w16_kb_2^22x100"] = {"ms": t, "Mleaf_per_s": (1 << 22) / t / 1e3, "Mperm_per_s": 58720255 / t / 1e3,
+                                                            "alg_GBps": 1.946e9 / (t * 1e-3) / 1e9, "launches": nl / k}
+        del xm
+        # config 5 leaf shape: Poseidon2-24 sponge + Poseidon2-16 compress over a 2^21 x 328 slice (quarter of 1312 columns)
+        xw = torch.randint(0, KB.P, (1 << 21, 328), device=dev, dtype=torch.int32, generator=g)
+        t, nl = timed(lambda: gpu.merkle_commit(KB.id, _lib.HASH_POSEIDON2_W24, [xw]), k, 1)
+        others["merkle_commit_poseidon2_w24_kb_2^21x328"] = {"ms": t, "Mperm_per_s": ((1 << 21) * 21 + (1 << 21) - 1) / t / 1e3}
+        del xw
+        # config 4 shape at 1/4 scale: BabyBear 2^20 x 300, LDE blowup 2 + Keccak Merkle (cap 3) + FRI commit phase on 2^21 EF4
+        xb = torch.randint(0, BB.P, (1 << 20, 300), device=dev, dtype=torch.int32, generator=g)
+        t, nl = timed(lambda: gpu.pcs_commit(BB.id, _lib.HASH_KECCAK, xb, 1), k, 1)
+        others["pcs_commit_keccak_bb_2^20x300"] = {"ms": t, "launches": nl / k}
+        del xb
+        betas = np.random.default_rng(2).integers(0, BB.P, size=(8, 4), dtype=np.uint32)
+        v0 = torch.randint(0, BB.P, (1 << 21, 4), device=dev, dtype=torch.int32, generator=g)
+        def fri():
+            gpu.fri_commit_phase(BB.id, _lib.HASH_KECCAK, v0.clone(), 1, 0, 3, 3, betas)
+        t, nl = timed(fri, k, 1)
+        others["fri_commit_phase_keccak_bb_2^21"] = {"ms": t, "launches": nl / k}
+        line["others"] = others
+
+    # ---- CPU baseline (rank 0, N=1)
+    if world == 1 and rank == 0 and not args.no_cpu:
+        try:
+            v, cores, sample = cpu_lde_throughput()
+            line["cpu_baseline"] = {"value": v, "unit": "Gelem/s", "cores": cores, "kind": "port", "sample": sample}
+        except Exception as e:  # the oracle is test infrastructure; never let it break the GPU numbers
+            line["cpu_baseline"] = {"value": None, "unit": "Gelem/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e}"}
+
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -184,7 +184,7 @@ int32_t p3gpu_poseidon2_set_constants(p3gpu_ctx *ctx, int field, int width, cons
     memset(&k, 0, sizeof k);
     for (int i = 0; i < 4 * width; i++) {
         P3_CHECK(rc_initial[i] < p && rc_terminal[i] < p, P3GPU_EINVAL, "round constant not in canonical Montgomery range");
-        k.rc_init[i] = rc_initial[i]; k.rc_term[i] = rc_terminal[i];
+        k.rc_ext[i] = rc_initial[i]; k.rc_ext[4 * width + i] = rc_terminal[i];
     }
     for (int i = 0; i < rounds_p; i++) {
         P3_CHECK(rc_internal[i] < p, P3GPU_EINVAL, "round constant not in canonical Montgomery range");

@@ -42,8 +42,7 @@ void set_error(const char *fmt, ...);
     } while (0)
 
 struct Poseidon2Consts {          // device layout consumed by the hash kernels
-    u32 rc_init[4 * 24];
-    u32 rc_term[4 * 24];
+    u32 rc_ext[8 * 24];  // external round r (0-3 initial, 4-7 terminal), element i at r * width + i
     u32 rc_int[32];
     int rounds_p;
     int width;

@@ -100,30 +100,30 @@ template <int F, int W, int I> struct DiagLoop {
 };
 template <int F, int W> struct DiagLoop<F, W, W> { static __device__ __forceinline__ void run(u32 (&)[W], u32) {} };
 
+// One copy of the external-round body and one of the internal-round body (rounds are loops, not unrolled): the fully
+// unrolled permutation is 50-300 KB of SASS and the leaf kernels then stall on instruction fetch (ncu: stall_no_instruction
+// was the top reason); looped, a whole sponge kernel is 10-20 KB and stays resident in the instruction cache.
 template <int F, int W>
 __device__ __forceinline__ void poseidon2_permute(u32 (&s)[W], const Poseidon2Consts &k) {
     mds_light<F, W>(s);
-#pragma unroll
-    for (int r = 0; r < 4; r++) {
-#pragma unroll
-        for (int i = 0; i < W; i++) s[i] = sbox<F>(fp_add<F>(s[i], k.rc_init[r * W + i]));
-        mds_light<F, W>(s);
-    }
-    // monty-31/src/poseidon2.rs:76-85
 #pragma unroll 1
-    for (int r = 0; r < k.rounds_p; r++) {
-        s[0] = sbox<F>(fp_add<F>(s[0], k.rc_int[r]));
-        u32 part = s[1];
+    for (int r = 0; r < 8; r++) {
+        if (r == 4) {
+            // monty-31/src/poseidon2.rs:76-85
+#pragma unroll 1
+            for (int q = 0; q < k.rounds_p; q++) {
+                s[0] = sbox<F>(fp_add<F>(s[0], k.rc_int[q]));
+                u32 part = s[1];
 #pragma unroll
-        for (int i = 2; i < W; i++) part = fp_add<F>(part, s[i]);
-        const u32 sum = fp_add<F>(part, s[0]);
-        s[0] = fp_sub<F>(part, s[0]);
-        DiagLoop<F, W, 1>::run(s, sum);
-    }
+                for (int i = 2; i < W; i++) part = fp_add<F>(part, s[i]);
+                const u32 sum = fp_add<F>(part, s[0]);
+                s[0] = fp_sub<F>(part, s[0]);
+                DiagLoop<F, W, 1>::run(s, sum);
+            }
+        }
+        // external round r (0-3 initial, 4-7 terminal): poseidon2/src/external.rs:288-336
 #pragma unroll
-    for (int r = 0; r < 4; r++) {
-#pragma unroll
-        for (int i = 0; i < W; i++) s[i] = sbox<F>(fp_add<F>(s[i], k.rc_term[r * W + i]));
+        for (int i = 0; i < W; i++) s[i] = sbox<F>(fp_add<F>(s[i], k.rc_ext[r * W + i]));
         mds_light<F, W>(s);
     }
 }
@@ -170,27 +170,23 @@ __global__ void __launch_bounds__(128) poseidon2_leaf_kernel(const __grid_consta
     u32 s[W];
 #pragma unroll
     for (int i = 0; i < W; i++) s[i] = 0;
-    if (a.n_mats == 1) {  // fast path: one matrix, contiguous row
-        const u32 w = a.width[0];
-        const u32 *row = a.ptr[0] + r * w;
-        u32 c0 = 0;
-        for (; c0 + RATE <= w; c0 += RATE) {
+    // one absorb/permute loop (a single inlined copy of the permutation) for both the one-matrix fast path and the
+    // multi-matrix stream (rows concatenated in input order, merkle_tree.rs:312-316)
+    const bool single = (a.n_mats == 1);
+    const u32 w0 = a.width[0];
+    const u32 *row0 = a.ptr[0] + r * w0;
+    RowCursor cur(a, r);
+    u32 c0 = 0;
+    while (single ? (c0 < w0) : cur.more()) {
+        if (single) {
 #pragma unroll
-            for (int i = 0; i < RATE; i++) s[i] = __ldg(row + c0 + i);
-            poseidon2_permute<F, W>(s, k);
-        }
-        if (c0 < w) {
-#pragma unroll
-            for (int i = 0; i < RATE; i++) if (c0 + i < w) s[i] = __ldg(row + c0 + i);
-            poseidon2_permute<F, W>(s, k);
-        }
-    } else {
-        RowCursor cur(a, r);
-        while (cur.more()) {
+            for (int i = 0; i < RATE; i++) if (c0 + i < w0) s[i] = __ldg(row0 + c0 + i);
+            c0 += RATE;
+        } else {
 #pragma unroll
             for (int i = 0; i < RATE; i++) if (cur.more()) s[i] = cur.next();
-            poseidon2_permute<F, W>(s, k);
         }
+        poseidon2_permute<F, W>(s, k);
     }
     uint4 *o = reinterpret_cast<uint4 *>(a.out + r * 8);
     o[0] = make_uint4(s[0], s[1], s[2], s[3]);
@@ -277,26 +273,20 @@ __global__ void __launch_bounds__(128) keccak_leaf_kernel(const __grid_constant_
     u64 s[25];
 #pragma unroll
     for (int i = 0; i < 25; i++) s[i] = 0;
-    if (a.n_mats == 1) {
-        const u32 w = a.width[0];
-        const u32 *row = a.ptr[0] + r * w;
-        u32 c0 = 0;
-        for (; c0 + 34 <= w; c0 += 34) {
-#pragma unroll
-            for (int i = 0; i < 17; i++) s[i] = (u64)__ldg(row + c0 + 2 * i) | ((u64)__ldg(row + c0 + 2 * i + 1) << 32);
-            keccak_f(s);
-        }
-        if (c0 < w) {
+    const bool single = (a.n_mats == 1);
+    const u32 w0 = a.width[0];
+    const u32 *row0 = a.ptr[0] + r * w0;
+    RowCursor cur(a, r);
+    u32 c0 = 0;
+    while (single ? (c0 < w0) : cur.more()) {
+        if (single) {
 #pragma unroll
             for (int i = 0; i < 17; i++) {
                 const u32 e = c0 + 2 * i;
-                if (e < w) s[i] = (u64)__ldg(row + e) | (e + 1 < w ? ((u64)__ldg(row + e + 1) << 32) : 0ull);
+                if (e < w0) s[i] = (u64)__ldg(row0 + e) | (e + 1 < w0 ? ((u64)__ldg(row0 + e + 1) << 32) : 0ull);
             }
-            keccak_f(s);
-        }
-    } else {
-        RowCursor cur(a, r);
-        while (cur.more()) {
+            c0 += 34;
+        } else {
 #pragma unroll
             for (int i = 0; i < 17; i++) {
                 if (cur.more()) {
@@ -305,8 +295,8 @@ __global__ void __launch_bounds__(128) keccak_leaf_kernel(const __grid_constant_
                     s[i] = lo | (hi << 32);
                 }
             }
-            keccak_f(s);
         }
+        keccak_f(s);
     }
     u64 *o = reinterpret_cast<u64 *>(a.out + r * 8);
     o[0] = s[0]; o[1] = s[1]; o[2] = s[2]; o[3] = s[3];

@@ -35,6 +35,9 @@ struct PassArgs {
     u32 w;         // row pitch in elements
     u32 col0;      // first column of this launch
     u32 n_ctiles;  // column tiles (of CT columns) in this launch
+    u32 ct;        // tile width of the generic-width kernel variant
+    u32 n_cosets;  // cosets batched in this launch (fastest-varying part of blockIdx.x)
+    u32 vec16;     // fast kernel: row segments are 16-byte aligned (cp.async 16)
     int log_n, l0, l1;
     const uint2 *tw;  // heap-ordered twiddles of coset 0
     int in_bitrev, out_bitrev;
@@ -93,8 +96,8 @@ __global__ void __launch_bounds__(THREADS) ntt_pass_kernel(const PassArgs a) {
     u32 *data = reinterpret_cast<u32 *>(smem_raw);
     uint2 *tws = reinterpret_cast<uint2 *>(data + ((size_t)R << LOG_CT));
 
-    const u32 ctile = blockIdx.x % a.n_ctiles, tile = blockIdx.x / a.n_ctiles;
-    const u32 coset = blockIdx.y;
+    const u32 coset = blockIdx.x % a.n_cosets, bx = blockIdx.x / a.n_cosets;
+    const u32 ctile = bx % a.n_ctiles, tile = bx / a.n_ctiles;
     const int lowbits = a.log_n - a.l1;
     const u32 L = tile & ((1u << lowbits) - 1u), T = tile >> lowbits;
     const u32 col = a.col0 + ctile * CT;
@@ -167,6 +170,169 @@ __global__ void __launch_bounds__(THREADS) ntt_pass_kernel(const PassArgs a) {
             if (a.final_reduce) v = fp_reduce<F>(v);
             out[(size_t)row * a.w + col + c] = v;
         }
+    }
+}
+
+// ---- fast path: the whole pass as TWO register networks with one shared-memory exchange ------------------------
+// For 7 <= r <= 10 the r layers split as Q1 + Q2 (Q2 = ceil(r/2) <= 5).  Step 1 loads 2^Q1 rows per thread straight from
+// global memory (stride 2^Q2 local rows), runs Q1 layers in registers and parks the results in shared memory; step 2
+// reads 2^Q2 consecutive local rows, runs Q2 layers and stores straight to global memory.  Per element and pass that is
+// one shared store + one shared load (the generic kernel does 2 per radix step plus the staging copy).
+// Shared layout: local row rho, column c at (rho >> Q2) * gstride + (rho & (2^Q2-1)) * CT + c with gstride = 2^Q2*CT + pad,
+// pad chosen so that gstride = CT (mod 32): both access patterns are bank-conflict free for ANY tile width CT, which lets
+// one launch class take a non-power-of-two remainder tile (e.g. 100 = 5 x 16 + 20 columns) without sector over-fetch.
+template <int Q> __host__ __device__ constexpr u32 brev_const(u32 m) {
+    u32 r = 0;
+    for (int b = 0; b < Q; b++) r |= ((m >> b) & 1u) << (Q - 1 - b);
+    return r;
+}
+
+template <int F, int Q>
+__device__ __forceinline__ void reg_network(u32 (&x)[1 << Q], const uint2 *tws, u32 node) {
+    constexpr int E = 1 << Q;
+#pragma unroll
+    for (int j = 0; j < Q; j++) {
+        const int half = E >> (j + 1);
+#pragma unroll
+        for (int grp = 0; grp < (1 << j); grp++) {
+            const uint2 z = tws[(node << j) + grp];
+#pragma unroll
+            for (int t = 0; t < half; t++) ct_butterfly<F>(x[grp * 2 * half + t], x[grp * 2 * half + t + half], z);
+        }
+    }
+}
+
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async8(void *smem, const void *gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async4(void *smem, const void *gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+// Persistent, double-buffered variant: a CTA walks over tiles; while it computes tile k from shared buffer k&1, the
+// cp.async (LDGSTS) copies of tile k+1 (data rows + its R-1 twiddles) are in flight into the other buffer, so HBM latency
+// is overlapped with the integer work instead of being serialised with it.  Step 1 runs in place in shared memory,
+// step 2 streams its results straight to global memory.
+template <int F, int R_LOG, int LOG_CT, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1) ntt_pass_fast_kernel(const __grid_constant__ PassArgs a) {
+    constexpr int Q2 = (R_LOG + 1) / 2, Q1 = R_LOG - Q2;
+    constexpr u32 E1 = 1u << Q1, E2 = 1u << Q2, R = 1u << R_LOG;
+    const u32 CT = LOG_CT >= 0 ? (1u << (LOG_CT >= 0 ? LOG_CT : 0)) : a.ct;
+    const u32 padw = (CT + 32u - ((E2 * CT) & 31u)) & 31u;
+    const u32 gstride = E2 * CT + padw;
+    const u32 buf_words = (E1 * gstride + 3u) & ~3u;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    u32 *data0 = reinterpret_cast<u32 *>(smem_raw);
+    uint2 *tws0 = reinterpret_cast<uint2 *>(data0 + 2 * buf_words);
+
+    const int lowbits = a.log_n - a.l1;
+    const int brsh = 32 - a.log_n;
+    const u32 n_row_tiles = 1u << (a.log_n - R_LOG);
+    const u32 total = n_row_tiles * a.n_ctiles * a.n_cosets;
+    const bool vec16 = a.vec16 != 0;
+
+    auto decode = [&](u32 t, u32 &coset, u32 &col, u32 &T, u32 &ibase) {
+        coset = t % a.n_cosets;
+        const u32 bx = t / a.n_cosets;
+        const u32 ctile = bx % a.n_ctiles, tile = bx / a.n_ctiles;
+        const u32 L = tile & ((1u << lowbits) - 1u);
+        T = tile >> lowbits;
+        col = a.col0 + ctile * CT;
+        ibase = (a.l0 == 0 ? 0u : (T << (a.log_n - a.l0))) | L;
+    };
+    auto issue = [&](u32 t, u32 buf) {
+        u32 coset, col, T, ibase;
+        decode(t, coset, col, T, ibase);
+        u32 *data = data0 + buf * buf_words;
+        uint2 *tws = tws0 + buf * R;
+        const uint2 *tw = a.tw + (size_t)coset * a.tw_stride;
+        const u32 *in = a.in + (size_t)coset * a.in_stride + col;
+        for (u32 k = threadIdx.x + 1; k < R; k += THREADS) {
+            const int lam = 31 - __clz(k);
+            const u32 ql = k - (1u << lam);
+            cp_async8(tws + k, tw + ((size_t)1 << (a.l0 + lam)) + ((size_t)T << lam) + ql);
+        }
+        if (vec16) {
+            const u32 cv = CT >> 2;
+            for (u32 it = threadIdx.x; it < R * cv; it += THREADS) {
+                const u32 rho = it / cv, c4 = it - rho * cv;
+                const u32 i = ibase | (rho << lowbits);
+                const u32 row = a.in_bitrev ? (__brev(i) >> brsh) : i;
+                cp_async16(data + (rho >> Q2) * gstride + (rho & (E2 - 1u)) * CT + 4 * c4, in + (size_t)row * a.w + 4 * c4);
+            }
+        } else {
+            for (u32 it = threadIdx.x; it < R * CT; it += THREADS) {
+                const u32 rho = it / CT, c = it - rho * CT;
+                const u32 i = ibase | (rho << lowbits);
+                const u32 row = a.in_bitrev ? (__brev(i) >> brsh) : i;
+                cp_async4(data + (rho >> Q2) * gstride + (rho & (E2 - 1u)) * CT + c, in + (size_t)row * a.w + c);
+            }
+        }
+        cp_async_commit();
+    };
+
+    u32 t = blockIdx.x;
+    if (t >= total) return;
+    issue(t, 0);
+    for (u32 k = 0; t < total; t += gridDim.x, k++) {
+        const u32 buf = k & 1u;
+        if (t + gridDim.x < total) { issue(t + gridDim.x, buf ^ 1u); cp_async_wait<1>(); }
+        else cp_async_wait<0>();
+        __syncthreads();
+        u32 *data = data0 + buf * buf_words;
+        const uint2 *tws = tws0 + buf * R;
+        u32 coset, col, T, ibase;
+        decode(t, coset, col, T, ibase);
+        // ---- step 1 (in place in shared memory): item it = g*CT + c holds local rows g + m*E2, m < E1
+        for (u32 it = threadIdx.x; it < E2 * CT; it += THREADS) {
+            u32 x[E1];
+#pragma unroll
+            for (u32 m = 0; m < E1; m++) x[m] = data[m * gstride + it];
+            if (a.has_scale) {
+#pragma unroll
+                for (u32 m = 0; m < E1; m++) x[m] = shoup_mul<F>(x[m], a.scale);
+            }
+            reg_network<F, Q1>(x, tws, 1u);
+#pragma unroll
+            for (u32 m = 0; m < E1; m++) data[m * gstride + it] = x[m];
+        }
+        __syncthreads();
+        // ---- step 2: shared -> registers -> global.  item = (g, c): local rows g*E2 + m, m < E2
+        {
+            // out row(m) = ((row0 + K_m * S) << out_sh) + out_add: natural: K_m = m, S = 1 << lowbits;
+            //                                                        bit-reversed: K_m = brev_Q2(m), S = 1 << (l0+Q1)
+            const size_t sstride = ((size_t)(a.out_bitrev ? (1u << (a.l0 + Q1)) : (1u << lowbits)) << a.out_sh) * a.w;
+            u32 *out = a.out + (size_t)coset * a.out_stride + col;
+            for (u32 it = threadIdx.x; it < E1 * CT; it += THREADS) {
+                u32 g, c;
+                if (LOG_CT >= 0) { g = it >> (LOG_CT >= 0 ? LOG_CT : 0); c = it & (CT - 1u); } else { g = it / CT; c = it - g * CT; }
+                const u32 *sp = data + g * gstride + c;
+                u32 x[E2];
+#pragma unroll
+                for (u32 m = 0; m < E2; m++) x[m] = sp[m * CT];
+                reg_network<F, Q2>(x, tws, E1 + g);
+                const u32 i0 = ibase | (g << (lowbits + Q2));
+                const u32 row0 = ((a.out_bitrev ? (__brev(i0) >> brsh) : i0) << a.out_sh) + a.out_add;
+                u32 *p = out + (size_t)row0 * a.w + c;
+                if (a.final_reduce) {
+#pragma unroll
+                    for (u32 m = 0; m < E2; m++) x[m] = fp_reduce<F>(x[m]);
+                }
+                if (a.out_bitrev) {
+#pragma unroll
+                    for (u32 m = 0; m < E2; m++) p[brev_const<Q2>(m) * sstride] = x[m];
+                } else {
+#pragma unroll
+                    for (u32 m = 0; m < E2; m++) p[m * sstride] = x[m];
+                }
+            }
+        }
+        __syncthreads();  // buffer `buf` may be refilled by the next iteration's cp.async
     }
 }
 
@@ -247,24 +413,76 @@ static int env_int(const char *name, int dflt) {
 }
 
 template <int F, int LOG_CT, bool VEC>
-static int32_t launch_pass_ct(p3gpu_ctx *ctx, const PassArgs &a, unsigned n_cosets) {
+static int32_t launch_pass_ct(p3gpu_ctx *ctx, const PassArgs &a) {
     constexpr int THREADS = 256;
     const int r = a.l1 - a.l0;
     const size_t smem = (((size_t)1 << r) << LOG_CT) * 4 + ((size_t)1 << r) * sizeof(uint2);
     auto kern = ntt_pass_kernel<F, LOG_CT, THREADS, VEC>;
     if (smem > 48 * 1024) P3_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const size_t tiles = ((size_t)1 << (a.log_n - r)) * a.n_ctiles;
+    const size_t tiles = ((size_t)1 << (a.log_n - r)) * a.n_ctiles * a.n_cosets;
     P3_CHECK(tiles < (1ull << 31), P3GPU_EINVAL, "ntt: grid too large");
-    dim3 grid((unsigned)tiles, n_cosets);
-    kern<<<grid, THREADS, smem, ctx->stream>>>(a);
+    kern<<<(unsigned)tiles, THREADS, smem, ctx->stream>>>(a);
     ctx->launches++;
     P3_CUDA(cudaGetLastError());
     return P3GPU_OK;
 }
 
-// One pass over all columns: columns are split greedily into tiles of main_ct, then narrower power-of-two tiles.
+template <int F, int R_LOG, int LOG_CT>
+static int32_t launch_fast_r(p3gpu_ctx *ctx, const PassArgs &a) {
+    constexpr int THREADS = 512;
+    constexpr int Q2 = (R_LOG + 1) / 2, Q1 = R_LOG - Q2;
+    const u32 ct = LOG_CT >= 0 ? (1u << (LOG_CT >= 0 ? LOG_CT : 0)) : a.ct;
+    const u32 e2 = 1u << Q2, e1 = 1u << Q1;
+    const u32 padw = (ct + 32u - ((e2 * ct) & 31u)) & 31u;
+    const size_t buf_words = ((size_t)e1 * (e2 * ct + padw) + 3) & ~(size_t)3;
+    const size_t smem = 2 * buf_words * 4 + 2 * ((size_t)1 << R_LOG) * sizeof(uint2);
+    auto kern = ntt_pass_fast_kernel<F, R_LOG, LOG_CT, THREADS>;
+    P3_CHECK(smem <= 227 * 1024, P3GPU_EINVAL, "ntt: tile does not fit shared memory");
+    if (smem > 48 * 1024) P3_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const size_t tiles = ((size_t)1 << (a.log_n - R_LOG)) * a.n_ctiles * a.n_cosets;
+    P3_CHECK(tiles < (1ull << 31), P3GPU_EINVAL, "ntt: grid too large");
+    // persistent grid: as many CTAs as fit (shared memory / 512 threads per CTA => at most 4 per SM)
+    size_t per_sm = std::min<size_t>(4, (227 * 1024) / (smem + 1024));
+    if (per_sm < 1) per_sm = 1;
+    const size_t grid = std::min(tiles, per_sm * (size_t)ctx->sm_count);
+    kern<<<(unsigned)grid, THREADS, smem, ctx->stream>>>(a);
+    ctx->launches++;
+    P3_CUDA(cudaGetLastError());
+    return P3GPU_OK;
+}
+template <int F, int LOG_CT>
+static int32_t launch_fast(p3gpu_ctx *ctx, const PassArgs &a) {
+    switch (a.l1 - a.l0) {
+        case 7: return launch_fast_r<F, 7, LOG_CT>(ctx, a);
+        case 8: return launch_fast_r<F, 8, LOG_CT>(ctx, a);
+        case 9: return launch_fast_r<F, 9, LOG_CT>(ctx, a);
+        default: return launch_fast_r<F, 10, LOG_CT>(ctx, a);
+    }
+}
+
+// One pass over all columns.
+//   fast path (7 <= r <= 10): tiles of 16 columns; a remainder of w mod 16 columns is merged into the last tile
+//   (one extra launch with a runtime tile width of 17..31, or 1..15 when w < 16).
+//   generic path: columns are split greedily into power-of-two tiles of main_ct, main_ct/2, ... columns.
 template <int F>
 static int32_t launch_pass(p3gpu_ctx *ctx, PassArgs a, unsigned n_cosets, int main_log_ct) {
+    a.n_cosets = n_cosets;
+    const int r = a.l1 - a.l0;
+    if (r >= 7 && r <= 10 && !env_int("P3GPU_NTT_GENERIC", 0)) {
+        // 16-column tiles; a remainder of <= 8 columns is merged into the last tile (runtime width 17..24),
+        // a larger remainder (9..15 columns) becomes its own tile.
+        const bool al16 = (a.w % 4 == 0) && (reinterpret_cast<uintptr_t>(a.in) % 16 == 0) && (a.in_stride % 4 == 0);
+        const u32 k = a.w / 16, rem = a.w % 16;
+        const bool merge = rem && rem <= 8 && k >= 1;
+        const u32 n16 = merge ? k - 1 : k;
+        if (n16) { a.col0 = 0; a.n_ctiles = n16; a.ct = 16; a.vec16 = al16; P3_TRY((launch_fast<F, 4>(ctx, a))); }
+        if (rem) {
+            a.col0 = n16 * 16; a.n_ctiles = 1; a.ct = a.w - n16 * 16;
+            a.vec16 = al16 && (a.ct % 4 == 0);
+            P3_TRY((launch_fast<F, -1>(ctx, a)));
+        }
+        return P3GPU_OK;
+    }
     const bool aligned = (a.w % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.in) | reinterpret_cast<uintptr_t>(a.out)) % 16 == 0) &&
                          ((a.in_stride | a.out_stride) % 4 == 0);
     u32 col = 0, rem = a.w;
@@ -272,16 +490,16 @@ static int32_t launch_pass(p3gpu_ctx *ctx, PassArgs a, unsigned n_cosets, int ma
         const u32 ct = 1u << lct;
         const u32 n = rem >> lct;
         if (!n) continue;
-        a.col0 = col; a.n_ctiles = n;
+        a.col0 = col; a.n_ctiles = n; a.ct = ct;
         const bool vec = aligned && lct >= 2 && (col % 4 == 0);
         int32_t rc;
         switch (lct) {
-            case 5: rc = vec ? launch_pass_ct<F, 5, true>(ctx, a, n_cosets) : launch_pass_ct<F, 5, false>(ctx, a, n_cosets); break;
-            case 4: rc = vec ? launch_pass_ct<F, 4, true>(ctx, a, n_cosets) : launch_pass_ct<F, 4, false>(ctx, a, n_cosets); break;
-            case 3: rc = vec ? launch_pass_ct<F, 3, true>(ctx, a, n_cosets) : launch_pass_ct<F, 3, false>(ctx, a, n_cosets); break;
-            case 2: rc = vec ? launch_pass_ct<F, 2, true>(ctx, a, n_cosets) : launch_pass_ct<F, 2, false>(ctx, a, n_cosets); break;
-            case 1: rc = launch_pass_ct<F, 1, false>(ctx, a, n_cosets); break;
-            default: rc = launch_pass_ct<F, 0, false>(ctx, a, n_cosets); break;
+            case 5: rc = vec ? launch_pass_ct<F, 5, true>(ctx, a) : launch_pass_ct<F, 5, false>(ctx, a); break;
+            case 4: rc = vec ? launch_pass_ct<F, 4, true>(ctx, a) : launch_pass_ct<F, 4, false>(ctx, a); break;
+            case 3: rc = vec ? launch_pass_ct<F, 3, true>(ctx, a) : launch_pass_ct<F, 3, false>(ctx, a); break;
+            case 2: rc = vec ? launch_pass_ct<F, 2, true>(ctx, a) : launch_pass_ct<F, 2, false>(ctx, a); break;
+            case 1: rc = launch_pass_ct<F, 1, false>(ctx, a); break;
+            default: rc = launch_pass_ct<F, 0, false>(ctx, a); break;
         }
         P3_TRY(rc);
         col += n * ct; rem -= n * ct;
@@ -312,7 +530,7 @@ template <int F>
 static int32_t run_network(p3gpu_ctx *ctx, int log_n, size_t w, const uint2 *tw, size_t tw_stride, unsigned n_cosets,
                            const u32 *src, size_t src_stride, int in_bitrev, u32 *dst, size_t dst_stride, int out_bitrev,
                            int out_sh, u32 out_add, u32 *tmp, bool has_scale, uint2 scale, bool final_reduce) {
-    const int max_r = std::min(12, std::max(4, env_int("P3GPU_NTT_MAXR", 11)));
+    const int max_r = std::min(12, std::max(4, env_int("P3GPU_NTT_MAXR", 10)));
     const int main_log_ct = std::min(5, std::max(0, env_int("P3GPU_NTT_LOGCT", 4)));
     const NetworkPlan plan = plan_passes(log_n, max_r);
     const bool remap = out_bitrev || out_sh != 0 || out_add != 0;
