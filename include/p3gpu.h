@@ -124,6 +124,12 @@ int32_t p3gpu_merkle_commit(p3gpu_ctx *ctx, int field, int hash, size_t n_mats, 
                             const size_t *heights, const size_t *widths, uint32_t *h_layers,
                             size_t *layer_lens, size_t *n_layers);
 
+/* Digest layers ABOVE an existing layer of n digests (d_digests, device): d_layers receives the (padded) copy of the input
+ * layer followed by every layer up to the root, p3gpu_merkle_total_digests(n) digests in all.  Used to finish a tree whose
+ * sub-tree roots were produced elsewhere (multi-GPU row sharding). */
+int32_t p3gpu_merkle_from_digests_dev(p3gpu_ctx *ctx, int field, int hash, const uint32_t *d_digests, size_t n,
+                                      uint32_t *d_layers, size_t *layer_lens, size_t *n_layers);
+
 /* ---- FRI -------------------------------------------------------------------------------------- */
 /* TwoAdicFriFolding::fold_matrix (two_adic_pcs.rs:134-213): rows x 2^log_arity EF4 values in bit-reversed
  * evaluation order -> rows EF4 values.  beta: 4 Montgomery words. */

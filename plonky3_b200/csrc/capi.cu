@@ -238,6 +238,12 @@ int32_t p3gpu_merkle_commit(p3gpu_ctx *ctx, int field, int hash, size_t n_mats, 
     return P3GPU_OK;
 }
 
+int32_t p3gpu_merkle_from_digests_dev(p3gpu_ctx *ctx, int field, int hash, const uint32_t *d_digests, size_t n, uint32_t *d_layers,
+                                      size_t *layer_lens, size_t *n_layers) {
+    P3_CHECK(ctx && d_digests && d_layers && layer_lens && n_layers, P3GPU_EINVAL, "null argument");
+    return hash_merkle_from_digests(ctx, field, hash, d_digests, n, d_layers, layer_lens, n_layers);
+}
+
 // ---- FRI ---------------------------------------------------------------------------------------
 int32_t p3gpu_fri_fold_dev(p3gpu_ctx *ctx, int field, const uint32_t *d_in, size_t rows, unsigned log_arity, const uint32_t beta[4],
                            uint32_t *d_out) {

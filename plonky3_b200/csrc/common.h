@@ -94,6 +94,8 @@ int32_t hash_keccak_f(p3gpu_ctx *ctx, u64 *d_states, size_t n);
 int32_t hash_merkle_commit(p3gpu_ctx *ctx, int field, int hash, size_t n_mats, const u32 *const *d_mats,
                            const size_t *heights, const size_t *widths, u32 *d_layers, size_t *layer_lens,
                            size_t *n_layers);
+int32_t hash_merkle_from_digests(p3gpu_ctx *ctx, int field, int hash, const u32 *d_digests, size_t n, u32 *d_layers,
+                                 size_t *layer_lens, size_t *n_layers);
 // fri.cu
 int32_t fri_fold(p3gpu_ctx *ctx, int field, const u32 *d_in, size_t rows, unsigned log_arity, const u32 beta[4], u32 *d_out);
 

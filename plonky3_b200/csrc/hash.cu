@@ -471,4 +471,29 @@ int32_t hash_merkle_commit(p3gpu_ctx *ctx, int field, int hash, size_t n_mats, c
     return P3GPU_OK;
 }
 
+// Layers above an existing digest layer (no matrices injected): used to finish a tree whose sub-tree roots were computed
+// elsewhere (multi-GPU row sharding: every rank compresses the gathered sub-tree roots redundantly).
+int32_t hash_merkle_from_digests(p3gpu_ctx *ctx, int field, int hash, const u32 *d_digests, size_t n, u32 *d_layers,
+                                 size_t *layer_lens, size_t *n_layers_out) {
+    P3_CHECK(hash >= P3GPU_HASH_POSEIDON2_W16 && hash <= P3GPU_HASH_KECCAK, P3GPU_EUNSUPPORTED, "unknown hash %d", hash);
+    P3_CHECK(n >= 1, P3GPU_EINVAL, "no digests");
+    size_t n_layers = 0;
+    size_t cur_len = padded_len2(n);
+    P3_CUDA(cudaMemcpyAsync(d_layers, d_digests, n * 32, cudaMemcpyDeviceToDevice, ctx->stream));
+    if (cur_len > n) P3_CUDA(cudaMemsetAsync(d_layers + n * 8, 0, (cur_len - n) * 32, ctx->stream));
+    u32 *cur = d_layers;
+    layer_lens[n_layers++] = cur_len;
+    while (cur_len > 1) {
+        const size_t raw_next = cur_len / 2, out_len = padded_len2(raw_next);
+        u32 *out = cur + cur_len * 8;
+        if (out_len > raw_next) P3_CUDA(cudaMemsetAsync(out + raw_next * 8, 0, (out_len - raw_next) * 32, ctx->stream));
+        P3_TRY(launch_compress(ctx, field, hash, cur, nullptr, 0, out, raw_next, 0));
+        P3_CHECK(n_layers < 64, P3GPU_EINVAL, "too many layers");
+        layer_lens[n_layers++] = out_len;
+        cur = out; cur_len = out_len;
+    }
+    *n_layers_out = n_layers;
+    return P3GPU_OK;
+}
+
 }  // namespace p3

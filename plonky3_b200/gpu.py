@@ -149,6 +149,18 @@ class Gpu:
             layers.append(out[off:off + lens[k]]); off += lens[k]
         return layers
 
+    def merkle_from_digests(self, field, hash_kind, digests_dev):
+        """Layers above an existing digest layer (CUDA tensor (n, 8)).  Returns [padded input layer, ..., root]."""
+        d = self._dev(digests_dev); self._use_torch_stream()
+        n = int(d.shape[0])
+        out = self._empty((self.merkle_total_digests(n), 8))
+        lens = (C.c_size_t * 65)(); nl = C.c_size_t()
+        check(self.L.p3gpu_merkle_from_digests_dev(self.h, field, hash_kind, d.data_ptr(), n, out.data_ptr(), lens, C.byref(nl)))
+        layers, off = [], 0
+        for k in range(nl.value):
+            layers.append(out[off:off + lens[k]]); off += lens[k]
+        return layers
+
     # ------------------------------------------------------------------ FRI
     def fri_fold(self, field, vec_ef, log_arity, beta):
         b = np.ascontiguousarray(beta, dtype=np.uint32)
