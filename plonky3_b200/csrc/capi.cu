@@ -34,6 +34,12 @@ int32_t ctx_scratch2(p3gpu_ctx *ctx, size_t bytes, void **out) {
     return P3GPU_OK;
 }
 
+int32_t ctx_pool(p3gpu_ctx *ctx, int slot, size_t bytes, void **out) {
+    P3_TRY(grow(&ctx->pool[slot], &ctx->pool_bytes[slot], bytes ? bytes : 1, ctx->stream));
+    *out = ctx->pool[slot];
+    return P3GPU_OK;
+}
+
 struct DevBuf {  // RAII device allocation for the host-pointer wrappers
     void *p = nullptr;
     ~DevBuf() { if (p) cudaFree(p); }
@@ -83,6 +89,7 @@ void p3gpu_ctx_destroy(p3gpu_ctx *ctx) {
     for (int f = 0; f < 2; f++) if (ctx->fold_table[f]) cudaFree(ctx->fold_table[f]);
     if (ctx->scratch) cudaFree(ctx->scratch);
     if (ctx->scratch2) cudaFree(ctx->scratch2);
+    for (int i = 0; i < 4; i++) if (ctx->pool[i]) cudaFree(ctx->pool[i]);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
@@ -144,11 +151,11 @@ int32_t p3gpu_dft_batch_dev(p3gpu_ctx *ctx, int field, int kind, const uint32_t 
 }
 int32_t p3gpu_dft_batch(p3gpu_ctx *ctx, int field, int kind, uint32_t *h_inout, size_t h, size_t w, uint32_t shift) {
     P3_CHECK(ctx && h_inout, P3GPU_EINVAL, "null argument");
-    DevBuf buf;
-    P3_TRY(buf.alloc(h * w * 4));
-    P3_CUDA(cudaMemcpyAsync(buf.p, h_inout, h * w * 4, cudaMemcpyHostToDevice, ctx->stream));
-    P3_TRY(ntt_dft_batch(ctx, field, kind, (const u32 *)buf.p, (u32 *)buf.p, h, w, shift));
-    P3_CUDA(cudaMemcpyAsync(h_inout, buf.p, h * w * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    void *buf = nullptr;
+    P3_TRY(ctx_pool(ctx, 0, h * w * 4, &buf));
+    P3_CUDA(cudaMemcpyAsync(buf, h_inout, h * w * 4, cudaMemcpyHostToDevice, ctx->stream));
+    P3_TRY(ntt_dft_batch(ctx, field, kind, (const u32 *)buf, (u32 *)buf, h, w, shift));
+    P3_CUDA(cudaMemcpyAsync(h_inout, buf, h * w * 4, cudaMemcpyDeviceToHost, ctx->stream));
     P3_CUDA(cudaStreamSynchronize(ctx->stream));
     return P3GPU_OK;
 }
@@ -161,13 +168,13 @@ int32_t p3gpu_coset_lde_batch(p3gpu_ctx *ctx, int field, const uint32_t *h_in, s
                               uint32_t shift, uint32_t *h_out, int bitrev_rows) {
     P3_CHECK(ctx && h_in && h_out, P3GPU_EINVAL, "null argument");
     P3_CHECK(added_bits <= 8, P3GPU_EINVAL, "added_bits %u too large", added_bits);
-    DevBuf in, out;
+    void *in = nullptr, *out = nullptr;
     const size_t nin = h * w * 4, nout = nin << added_bits;
-    P3_TRY(in.alloc(nin));
-    P3_TRY(out.alloc(nout));
-    P3_CUDA(cudaMemcpyAsync(in.p, h_in, nin, cudaMemcpyHostToDevice, ctx->stream));
-    P3_TRY(ntt_coset_lde(ctx, field, (const u32 *)in.p, h, w, added_bits, shift, (u32 *)out.p, bitrev_rows));
-    P3_CUDA(cudaMemcpyAsync(h_out, out.p, nout, cudaMemcpyDeviceToHost, ctx->stream));
+    P3_TRY(ctx_pool(ctx, 0, nin, &in));
+    P3_TRY(ctx_pool(ctx, 1, nout, &out));
+    P3_CUDA(cudaMemcpyAsync(in, h_in, nin, cudaMemcpyHostToDevice, ctx->stream));
+    P3_TRY(ntt_coset_lde(ctx, field, (const u32 *)in, h, w, added_bits, shift, (u32 *)out, bitrev_rows));
+    P3_CUDA(cudaMemcpyAsync(h_out, out, nout, cudaMemcpyDeviceToHost, ctx->stream));
     P3_CUDA(cudaStreamSynchronize(ctx->stream));
     return P3GPU_OK;
 }
@@ -254,13 +261,13 @@ int32_t p3gpu_fri_fold(p3gpu_ctx *ctx, int field, const uint32_t *h_in, size_t r
                        uint32_t *h_out) {
     P3_CHECK(ctx && h_in && h_out && beta, P3GPU_EINVAL, "null argument");
     P3_CHECK(log_arity >= 1 && log_arity <= 4, P3GPU_EINVAL, "log_arity %u out of range 1..4", log_arity);
-    DevBuf in, out;
+    void *in = nullptr, *out = nullptr;
     const size_t nin = (rows << log_arity) * 16;
-    P3_TRY(in.alloc(nin));
-    P3_TRY(out.alloc(rows * 16));
-    P3_CUDA(cudaMemcpyAsync(in.p, h_in, nin, cudaMemcpyHostToDevice, ctx->stream));
-    P3_TRY(fri_fold(ctx, field, (const u32 *)in.p, rows, log_arity, beta, (u32 *)out.p));
-    P3_CUDA(cudaMemcpyAsync(h_out, out.p, rows * 16, cudaMemcpyDeviceToHost, ctx->stream));
+    P3_TRY(ctx_pool(ctx, 0, nin, &in));
+    P3_TRY(ctx_pool(ctx, 1, rows * 16, &out));
+    P3_CUDA(cudaMemcpyAsync(in, h_in, nin, cudaMemcpyHostToDevice, ctx->stream));
+    P3_TRY(fri_fold(ctx, field, (const u32 *)in, rows, log_arity, beta, (u32 *)out));
+    P3_CUDA(cudaMemcpyAsync(h_out, out, rows * 16, cudaMemcpyDeviceToHost, ctx->stream));
     P3_CUDA(cudaStreamSynchronize(ctx->stream));
     return P3GPU_OK;
 }
@@ -282,10 +289,8 @@ int32_t p3gpu_fri_commit_phase_dev(p3gpu_ctx *ctx, int field, int hash, uint32_t
     // digest layers of the largest round + ping-pong buffer for the folded vector
     const unsigned la0 = log2_floor(len) > log_final ? log_arity_for_round(log2_floor(len), log_final, max_log_arity) : 1;
     void *layers = nullptr, *pong = nullptr;
-    DevBuf layers_buf, pong_buf;
-    P3_TRY(layers_buf.alloc(p3gpu_merkle_total_digests(len >> la0) * 32));
-    P3_TRY(pong_buf.alloc((len >> la0) * 16 + 16));
-    layers = layers_buf.p; pong = pong_buf.p;
+    P3_TRY(ctx_pool(ctx, 2, p3gpu_merkle_total_digests(len >> la0) * 32, &layers));
+    P3_TRY(ctx_pool(ctx, 3, (len >> la0) * 16 + 16, &pong));
     u32 *cur = d_vec, *other = (u32 *)pong;
     size_t cur_len = len, round = 0, cap_off = 0;
     while (cur_len > ((size_t)1 << log_final)) {

@@ -90,7 +90,7 @@ __device__ __forceinline__ void radix_step(u32 *data, const uint2 *tws, int r, i
 template <int F, int LOG_CT, int THREADS, bool VEC>
 __global__ void __launch_bounds__(THREADS) ntt_pass_kernel(const PassArgs a) {
     constexpr u32 CT = 1u << LOG_CT;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     const int r = a.l1 - a.l0;
     const u32 R = 1u << r;
     u32 *data = reinterpret_cast<u32 *>(smem_raw);
@@ -214,19 +214,23 @@ __device__ __forceinline__ void cp_async4(void *smem, const void *gmem) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
-// Persistent, double-buffered variant: a CTA walks over tiles; while it computes tile k from shared buffer k&1, the
-// cp.async (LDGSTS) copies of tile k+1 (data rows + its R-1 twiddles) are in flight into the other buffer, so HBM latency
-// is overlapped with the integer work instead of being serialised with it.  Step 1 runs in place in shared memory,
-// step 2 streams its results straight to global memory.
-template <int F, int R_LOG, int LOG_CT, int THREADS>
+// Persistent, double-buffered pass kernel.  A CTA (one per SM) walks over tiles of 2^R_LOG rows x `ct` columns:
+//   * tile k+1 (rows as 16-byte cp.async/LDGSTS copies, plus its 2^R_LOG - 1 twiddles) streams into the second shared
+//     buffer while tile k is computed, so HBM latency overlaps the integer work;
+//   * step 1 runs Q1 layers in registers IN PLACE in shared memory, step 2 runs Q2 layers and streams the results to
+//     global memory (per-row TMA bulk stores were tried and rejected: UBLKCP is a warp-uniform instruction, so one
+//     copy per lane serialises into a 32-iteration R2UR/PLOP3 loop per warp: +25 % instructions, profiles/README.md);
+//   * all tiles of a pass have the same runtime width ct (16/20/24 columns; w = 100 -> 5 x 20) so that ONE launch covers
+//     every column and neighbouring tiles share DRAM bursts through L2.
+template <int F, int R_LOG, int CT_T, int THREADS>   // CT_T: compile-time tile width (16/20/24) or 0 = runtime a.ct
 __global__ void __launch_bounds__(THREADS, 1) ntt_pass_fast_kernel(const __grid_constant__ PassArgs a) {
     constexpr int Q2 = (R_LOG + 1) / 2, Q1 = R_LOG - Q2;
     constexpr u32 E1 = 1u << Q1, E2 = 1u << Q2, R = 1u << R_LOG;
-    const u32 CT = LOG_CT >= 0 ? (1u << (LOG_CT >= 0 ? LOG_CT : 0)) : a.ct;
+    const u32 CT = CT_T ? (u32)CT_T : a.ct;
     const u32 padw = (CT + 32u - ((E2 * CT) & 31u)) & 31u;
     const u32 gstride = E2 * CT + padw;
     const u32 buf_words = (E1 * gstride + 3u) & ~3u;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     u32 *data0 = reinterpret_cast<u32 *>(smem_raw);
     uint2 *tws0 = reinterpret_cast<uint2 *>(data0 + 2 * buf_words);
 
@@ -234,43 +238,54 @@ __global__ void __launch_bounds__(THREADS, 1) ntt_pass_fast_kernel(const __grid_
     const int brsh = 32 - a.log_n;
     const u32 n_row_tiles = 1u << (a.log_n - R_LOG);
     const u32 total = n_row_tiles * a.n_ctiles * a.n_cosets;
-    const bool vec16 = a.vec16 != 0;
+    const bool vec16 = a.vec16 != 0;       // row segments 16-byte aligned in global memory (loads AND stores)
+    const bool shared_tw = (a.l0 == 0);    // first pass of a network: every tile uses the same twiddles
 
-    auto decode = [&](u32 t, u32 &coset, u32 &col, u32 &T, u32 &ibase) {
+    auto decode = [&](u32 t, u32 &coset, u32 &col, u32 &cw, u32 &T, u32 &ibase) {
         coset = t % a.n_cosets;
         const u32 bx = t / a.n_cosets;
         const u32 ctile = bx % a.n_ctiles, tile = bx / a.n_ctiles;
         const u32 L = tile & ((1u << lowbits) - 1u);
         T = tile >> lowbits;
-        col = a.col0 + ctile * CT;
+        col = ctile * CT;
+        cw = min(CT, a.w - col);
         ibase = (a.l0 == 0 ? 0u : (T << (a.log_n - a.l0))) | L;
     };
-    auto issue = [&](u32 t, u32 buf) {
-        u32 coset, col, T, ibase;
-        decode(t, coset, col, T, ibase);
-        u32 *data = data0 + buf * buf_words;
-        uint2 *tws = tws0 + buf * R;
+    auto issue_twiddles = [&](u32 coset, u32 T, uint2 *tws) {
         const uint2 *tw = a.tw + (size_t)coset * a.tw_stride;
-        const u32 *in = a.in + (size_t)coset * a.in_stride + col;
         for (u32 k = threadIdx.x + 1; k < R; k += THREADS) {
             const int lam = 31 - __clz(k);
             const u32 ql = k - (1u << lam);
             cp_async8(tws + k, tw + ((size_t)1 << (a.l0 + lam)) + ((size_t)T << lam) + ql);
         }
-        if (vec16) {
-            const u32 cv = CT >> 2;
-            for (u32 it = threadIdx.x; it < R * cv; it += THREADS) {
-                const u32 rho = it / cv, c4 = it - rho * cv;
-                const u32 i = ibase | (rho << lowbits);
-                const u32 row = a.in_bitrev ? (__brev(i) >> brsh) : i;
-                cp_async16(data + (rho >> Q2) * gstride + (rho & (E2 - 1u)) * CT + 4 * c4, in + (size_t)row * a.w + 4 * c4);
-            }
-        } else {
-            for (u32 it = threadIdx.x; it < R * CT; it += THREADS) {
-                const u32 rho = it / CT, c = it - rho * CT;
-                const u32 i = ibase | (rho << lowbits);
-                const u32 row = a.in_bitrev ? (__brev(i) >> brsh) : i;
-                cp_async4(data + (rho >> Q2) * gstride + (rho & (E2 - 1u)) * CT + c, in + (size_t)row * a.w + c);
+    };
+    auto issue = [&](u32 t, u32 buf) {
+        u32 coset, col, cw, T, ibase;
+        decode(t, coset, col, cw, T, ibase);
+        u32 *data = data0 + buf * buf_words;
+        const u32 *in = a.in + (size_t)coset * a.in_stride + col;
+        if (!shared_tw || a.n_cosets > 1) issue_twiddles(coset, T, tws0 + buf * R);
+        // chunk = 16 bytes (4 columns) when aligned, else one element
+        const u32 cpr = vec16 ? (cw >> 2) : cw;                  // chunks per row segment
+        const u32 rs = (THREADS / cpr) & ~(E2 - 1u);             // rows per sweep: a multiple of E2 keeps the shared address linear
+        const u32 nthr = rs * cpr;
+        if (threadIdx.x < nthr) {
+            const u32 rho0 = threadIdx.x / cpr, ch = threadIdx.x - rho0 * cpr;
+            const u32 e = vec16 ? 4u * ch : ch;
+            u32 *dst = data + (rho0 >> Q2) * gstride + (rho0 & (E2 - 1u)) * CT + e;
+            const u32 dstep = (rs >> Q2) * gstride;
+            if (!a.in_bitrev) {
+                const u32 *src = in + (size_t)(ibase | (rho0 << lowbits)) * a.w + e;
+                const size_t sstep = ((size_t)rs << lowbits) * a.w;
+                for (u32 rho = rho0; rho < R; rho += rs, dst += dstep, src += sstep) {
+                    if (vec16) cp_async16(dst, src); else cp_async4(dst, src);
+                }
+            } else {
+                for (u32 rho = rho0; rho < R; rho += rs, dst += dstep) {
+                    const u32 row = __brev(ibase | (rho << lowbits)) >> brsh;
+                    const u32 *src = in + (size_t)row * a.w + e;
+                    if (vec16) cp_async16(dst, src); else cp_async4(dst, src);
+                }
             }
         }
         cp_async_commit();
@@ -278,61 +293,72 @@ __global__ void __launch_bounds__(THREADS, 1) ntt_pass_fast_kernel(const __grid_
 
     u32 t = blockIdx.x;
     if (t >= total) return;
+    if (shared_tw && a.n_cosets == 1) issue_twiddles(0, 0, tws0);   // once per CTA, lands with the first tile's group
     issue(t, 0);
     for (u32 k = 0; t < total; t += gridDim.x, k++) {
         const u32 buf = k & 1u;
+        __syncthreads();   // every warp is done reading buffer buf^1 (tile k-1): it may be refilled
         if (t + gridDim.x < total) { issue(t + gridDim.x, buf ^ 1u); cp_async_wait<1>(); }
         else cp_async_wait<0>();
         __syncthreads();
         u32 *data = data0 + buf * buf_words;
-        const uint2 *tws = tws0 + buf * R;
-        u32 coset, col, T, ibase;
-        decode(t, coset, col, T, ibase);
-        // ---- step 1 (in place in shared memory): item it = g*CT + c holds local rows g + m*E2, m < E1
-        for (u32 it = threadIdx.x; it < E2 * CT; it += THREADS) {
-            u32 x[E1];
+        const uint2 *tws = (shared_tw && a.n_cosets == 1) ? tws0 : tws0 + buf * R;
+        u32 coset, col, cw, T, ibase;
+        decode(t, coset, col, cw, T, ibase);
+        const u32 dg = THREADS / cw, dc = THREADS - dg * cw;
+        // ---- step 1 (in place in shared memory): item (g, c) holds local rows g + m*E2, m < E1
+        {
+            u32 g = threadIdx.x / cw, c = threadIdx.x - g * cw;
+            for (; g < E2; ) {
+                u32 *sp = data + g * CT + c;
+                u32 x[E1];
 #pragma unroll
-            for (u32 m = 0; m < E1; m++) x[m] = data[m * gstride + it];
-            if (a.has_scale) {
+                for (u32 m = 0; m < E1; m++) x[m] = sp[m * gstride];
+                if (a.has_scale) {
 #pragma unroll
-                for (u32 m = 0; m < E1; m++) x[m] = shoup_mul<F>(x[m], a.scale);
+                    for (u32 m = 0; m < E1; m++) x[m] = shoup_mul<F>(x[m], a.scale);
+                }
+                reg_network<F, Q1>(x, tws, 1u);
+#pragma unroll
+                for (u32 m = 0; m < E1; m++) sp[m * gstride] = x[m];
+                c += dc; g += dg;
+                if (c >= cw) { c -= cw; g++; }
             }
-            reg_network<F, Q1>(x, tws, 1u);
-#pragma unroll
-            for (u32 m = 0; m < E1; m++) data[m * gstride + it] = x[m];
         }
         __syncthreads();
-        // ---- step 2: shared -> registers -> global.  item = (g, c): local rows g*E2 + m, m < E2
+        // ---- step 2: item (g, c) holds local rows g*E2 + m, m < E2
         {
+            u32 *out = a.out + (size_t)coset * a.out_stride + col;
             // out row(m) = ((row0 + K_m * S) << out_sh) + out_add: natural: K_m = m, S = 1 << lowbits;
             //                                                        bit-reversed: K_m = brev_Q2(m), S = 1 << (l0+Q1)
             const size_t sstride = ((size_t)(a.out_bitrev ? (1u << (a.l0 + Q1)) : (1u << lowbits)) << a.out_sh) * a.w;
-            u32 *out = a.out + (size_t)coset * a.out_stride + col;
-            for (u32 it = threadIdx.x; it < E1 * CT; it += THREADS) {
-                u32 g, c;
-                if (LOG_CT >= 0) { g = it >> (LOG_CT >= 0 ? LOG_CT : 0); c = it & (CT - 1u); } else { g = it / CT; c = it - g * CT; }
-                const u32 *sp = data + g * gstride + c;
+            u32 g = threadIdx.x / cw, c = threadIdx.x - g * cw;
+            for (; g < E1; ) {
+                u32 *sp = data + g * gstride + c;
                 u32 x[E2];
 #pragma unroll
                 for (u32 m = 0; m < E2; m++) x[m] = sp[m * CT];
                 reg_network<F, Q2>(x, tws, E1 + g);
-                const u32 i0 = ibase | (g << (lowbits + Q2));
-                const u32 row0 = ((a.out_bitrev ? (__brev(i0) >> brsh) : i0) << a.out_sh) + a.out_add;
-                u32 *p = out + (size_t)row0 * a.w + c;
                 if (a.final_reduce) {
 #pragma unroll
                     for (u32 m = 0; m < E2; m++) x[m] = fp_reduce<F>(x[m]);
                 }
-                if (a.out_bitrev) {
+                {
+                    const u32 i0 = ibase | (g << (lowbits + Q2));
+                    const u32 row0 = ((a.out_bitrev ? (__brev(i0) >> brsh) : i0) << a.out_sh) + a.out_add;
+                    u32 *p = out + (size_t)row0 * a.w + c;
+                    if (a.out_bitrev) {
 #pragma unroll
-                    for (u32 m = 0; m < E2; m++) p[brev_const<Q2>(m) * sstride] = x[m];
-                } else {
+                        for (u32 m = 0; m < E2; m++) p[brev_const<Q2>(m) * sstride] = x[m];
+                    } else {
 #pragma unroll
-                    for (u32 m = 0; m < E2; m++) p[m * sstride] = x[m];
+                        for (u32 m = 0; m < E2; m++) p[m * sstride] = x[m];
+                    }
                 }
+                c += dc; g += dg;
+                if (c >= cw) { c -= cw; g++; }
             }
         }
-        __syncthreads();  // buffer `buf` may be refilled by the next iteration's cp.async
     }
 }
 
@@ -427,22 +453,21 @@ static int32_t launch_pass_ct(p3gpu_ctx *ctx, const PassArgs &a) {
     return P3GPU_OK;
 }
 
-template <int F, int R_LOG, int LOG_CT>
-static int32_t launch_fast_r(p3gpu_ctx *ctx, const PassArgs &a) {
-    constexpr int THREADS = 512;
+template <int F, int R_LOG, int CT_T, int THREADS>
+static int32_t launch_fast_rct(p3gpu_ctx *ctx, const PassArgs &a) {
     constexpr int Q2 = (R_LOG + 1) / 2, Q1 = R_LOG - Q2;
-    const u32 ct = LOG_CT >= 0 ? (1u << (LOG_CT >= 0 ? LOG_CT : 0)) : a.ct;
+    const u32 ct = a.ct;
     const u32 e2 = 1u << Q2, e1 = 1u << Q1;
     const u32 padw = (ct + 32u - ((e2 * ct) & 31u)) & 31u;
     const size_t buf_words = ((size_t)e1 * (e2 * ct + padw) + 3) & ~(size_t)3;
     const size_t smem = 2 * buf_words * 4 + 2 * ((size_t)1 << R_LOG) * sizeof(uint2);
-    auto kern = ntt_pass_fast_kernel<F, R_LOG, LOG_CT, THREADS>;
+    auto kern = ntt_pass_fast_kernel<F, R_LOG, CT_T, THREADS>;
     P3_CHECK(smem <= 227 * 1024, P3GPU_EINVAL, "ntt: tile does not fit shared memory");
     if (smem > 48 * 1024) P3_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const size_t tiles = ((size_t)1 << (a.log_n - R_LOG)) * a.n_ctiles * a.n_cosets;
     P3_CHECK(tiles < (1ull << 31), P3GPU_EINVAL, "ntt: grid too large");
-    // persistent grid: as many CTAs as fit (shared memory / 512 threads per CTA => at most 4 per SM)
-    size_t per_sm = std::min<size_t>(4, (227 * 1024) / (smem + 1024));
+    // persistent grid: one CTA per SM (more when the tile is small enough for several to be resident)
+    size_t per_sm = std::min<size_t>(2, (227 * 1024) / (smem + 1024));
     if (per_sm < 1) per_sm = 1;
     const size_t grid = std::min(tiles, per_sm * (size_t)ctx->sm_count);
     kern<<<(unsigned)grid, THREADS, smem, ctx->stream>>>(a);
@@ -450,38 +475,58 @@ static int32_t launch_fast_r(p3gpu_ctx *ctx, const PassArgs &a) {
     P3_CUDA(cudaGetLastError());
     return P3GPU_OK;
 }
-template <int F, int LOG_CT>
+template <int F, int R_LOG, int CT_T>
+static int32_t launch_fast_rc(p3gpu_ctx *ctx, const PassArgs &a) {
+    static const int threads = env_int("P3GPU_NTT_THREADS", 512);
+    if (threads == 768) return launch_fast_rct<F, R_LOG, CT_T, 768>(ctx, a);
+    return launch_fast_rct<F, R_LOG, CT_T, 512>(ctx, a);
+}
+template <int F, int R_LOG>
+static int32_t launch_fast_r(p3gpu_ctx *ctx, const PassArgs &a) {
+    switch (a.ct) {   // compile-time widths keep every shared-memory offset an immediate
+        case 16: return launch_fast_rc<F, R_LOG, 16>(ctx, a);
+        case 20: return launch_fast_rc<F, R_LOG, 20>(ctx, a);
+        case 24: return launch_fast_rc<F, R_LOG, 24>(ctx, a);
+        default: return launch_fast_rc<F, R_LOG, 0>(ctx, a);
+    }
+}
+template <int F>
 static int32_t launch_fast(p3gpu_ctx *ctx, const PassArgs &a) {
     switch (a.l1 - a.l0) {
-        case 7: return launch_fast_r<F, 7, LOG_CT>(ctx, a);
-        case 8: return launch_fast_r<F, 8, LOG_CT>(ctx, a);
-        case 9: return launch_fast_r<F, 9, LOG_CT>(ctx, a);
-        default: return launch_fast_r<F, 10, LOG_CT>(ctx, a);
+        case 7: return launch_fast_r<F, 7>(ctx, a);
+        case 8: return launch_fast_r<F, 8>(ctx, a);
+        case 9: return launch_fast_r<F, 9>(ctx, a);
+        default: return launch_fast_r<F, 10>(ctx, a);
     }
 }
 
+// Column tile width of the fast kernel: all tiles of a launch share one width (a ragged last tile is allowed).
+// Prefer exact divisors that keep 16-byte alignment (16, 20, 24 columns = 64/80/96-byte row segments).
+static u32 choose_tile_width(u32 w) {
+    if (w <= 24) return w;
+    for (u32 ct : {16u, 20u, 24u, 12u})
+        if (w % ct == 0) return ct;
+    const u32 n = (w + 19) / 20;                 // ~20 columns per tile, nearly equal tiles
+    u32 ct = (w + n - 1) / n;
+    ct = (ct + 3) & ~3u;
+    return ct > 24 ? 24 : ct;
+}
+
 // One pass over all columns.
-//   fast path (7 <= r <= 10): tiles of 16 columns; a remainder of w mod 16 columns is merged into the last tile
-//   (one extra launch with a runtime tile width of 17..31, or 1..15 when w < 16).
+//   fast path (7 <= r <= 10): ONE launch, tiles of choose_tile_width(w) columns (16/20/24; ragged last tile allowed).
 //   generic path: columns are split greedily into power-of-two tiles of main_ct, main_ct/2, ... columns.
 template <int F>
 static int32_t launch_pass(p3gpu_ctx *ctx, PassArgs a, unsigned n_cosets, int main_log_ct) {
     a.n_cosets = n_cosets;
     const int r = a.l1 - a.l0;
     if (r >= 7 && r <= 10 && !env_int("P3GPU_NTT_GENERIC", 0)) {
-        // 16-column tiles; a remainder of <= 8 columns is merged into the last tile (runtime width 17..24),
-        // a larger remainder (9..15 columns) becomes its own tile.
-        const bool al16 = (a.w % 4 == 0) && (reinterpret_cast<uintptr_t>(a.in) % 16 == 0) && (a.in_stride % 4 == 0);
-        const u32 k = a.w / 16, rem = a.w % 16;
-        const bool merge = rem && rem <= 8 && k >= 1;
-        const u32 n16 = merge ? k - 1 : k;
-        if (n16) { a.col0 = 0; a.n_ctiles = n16; a.ct = 16; a.vec16 = al16; P3_TRY((launch_fast<F, 4>(ctx, a))); }
-        if (rem) {
-            a.col0 = n16 * 16; a.n_ctiles = 1; a.ct = a.w - n16 * 16;
-            a.vec16 = al16 && (a.ct % 4 == 0);
-            P3_TRY((launch_fast<F, -1>(ctx, a)));
-        }
-        return P3GPU_OK;
+        const u32 ct = choose_tile_width(a.w);
+        // 16-byte cp.async / TMA bulk stores need every row segment of every tile 16-byte aligned on both sides
+        const bool al16 = (a.w % 4 == 0) && (ct % 4 == 0) &&
+                          ((reinterpret_cast<uintptr_t>(a.in) | reinterpret_cast<uintptr_t>(a.out)) % 16 == 0) &&
+                          ((a.in_stride | a.out_stride) % 4 == 0);
+        a.col0 = 0; a.ct = ct; a.n_ctiles = (a.w + ct - 1) / ct; a.vec16 = al16;
+        return launch_fast<F>(ctx, a);
     }
     const bool aligned = (a.w % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.in) | reinterpret_cast<uintptr_t>(a.out)) % 16 == 0) &&
                          ((a.in_stride | a.out_stride) % 4 == 0);
