@@ -110,14 +110,18 @@ static unsigned log2_strict(size_t n) {
 }
 void p3o_reverse_matrix_index_bits(u32 *mat, size_t h, size_t w) {
     unsigned lh = log2_strict(h);
-    u32 *tmp = (u32 *)malloc(w * sizeof(u32));
-    for (size_t i = 0; i < h; i++) {
-        size_t j = bitrev(i, lh);
-        if (i < j) {
-            memcpy(tmp, mat + i * w, w * 4); memcpy(mat + i * w, mat + j * w, w * 4); memcpy(mat + j * w, tmp, w * 4);
+    #pragma omp parallel
+    {
+        u32 *tmp = (u32 *)malloc(w * sizeof(u32));
+        #pragma omp for schedule(static)
+        for (size_t i = 0; i < h; i++) {
+            size_t j = bitrev(i, lh);
+            if (i < j) {   /* each unordered pair is swapped by exactly one iteration: no races (matrix/src/util.rs:46-56) */
+                memcpy(tmp, mat + i * w, w * 4); memcpy(mat + i * w, mat + j * w, w * 4); memcpy(mat + j * w, tmp, w * 4);
+            }
         }
+        free(tmp);
     }
-    free(tmp);
 }
 
 /* ------------------------------------------------------------------------------------------------
@@ -145,7 +149,17 @@ void p3o_naive_dft(int fi, const u32 *in, size_t h, size_t w, u32 *out) {
     free(pw);
 }
 
-/* in-place forward DFT of every column with the given primitive h-th root; natural in, natural out */
+static inline void bf_rows(const field_t *f, u32 *a, u32 *b, size_t w, u32 t, int trivial) {
+    if (trivial) {
+        for (size_t c = 0; c < w; c++) { u32 x = a[c], y = b[c]; a[c] = f_add(f, x, y); b[c] = f_sub(f, x, y); }
+    } else {
+        for (size_t c = 0; c < w; c++) { u32 x = a[c], y = f_mul(f, b[c], t); a[c] = f_add(f, x, y); b[c] = f_sub(f, x, y); }
+    }
+}
+/* in-place forward DFT of every column with the given primitive h-th root; natural in, natural out.
+ * Textbook radix-2 DIT after a row bit-reversal, run as two cache-blocked halves like the reference's
+ * Radix2DitParallel (dft/src/radix_2_dit_parallel.rs:22-28): layers 0..mid-1 inside blocks of 2^mid consecutive rows,
+ * layers mid..log_h-1 inside the 2^mid interleaved row sets {q*2^mid + r}. Each half is one sweep over the matrix. */
 static void dft_rows(const field_t *f, u32 *mat, size_t h, size_t w, u32 root) {
     if (h <= 1) return;
     unsigned lh = log2_strict(h);
@@ -153,18 +167,28 @@ static void dft_rows(const field_t *f, u32 *mat, size_t h, size_t w, u32 root) {
     u32 *tw = (u32 *)malloc((h / 2) * 4);
     tw[0] = f_one(f);
     for (size_t i = 1; i < h / 2; i++) tw[i] = f_mul(f, tw[i - 1], root);
-    for (unsigned layer = 0; layer < lh; layer++) {
-        size_t half = (size_t)1 << layer, step = h >> (layer + 1);
-        #pragma omp parallel for schedule(static)
-        for (size_t pair = 0; pair < h / 2; pair++) {
-            size_t blk = pair >> layer, j = pair & (half - 1);
-            u32 *a = mat + (blk * 2 * half + j) * w, *b = a + half * w;
-            u32 t = tw[j * step];
-            if (j == 0) {
-                for (size_t c = 0; c < w; c++) { u32 x = a[c], y = b[c]; a[c] = f_add(f, x, y); b[c] = f_sub(f, x, y); }
-            } else {
-                for (size_t c = 0; c < w; c++) { u32 x = a[c], y = f_mul(f, b[c], t); a[c] = f_add(f, x, y); b[c] = f_sub(f, x, y); }
-            }
+    unsigned mid = (lh + 1) / 2;
+    size_t B = (size_t)1 << mid, nblk = h >> mid;
+    #pragma omp parallel for schedule(static)
+    for (size_t blk = 0; blk < nblk; blk++) {
+        u32 *base = mat + blk * B * w;
+        for (unsigned layer = 0; layer < mid; layer++) {
+            size_t half = (size_t)1 << layer, step = h >> (layer + 1);
+            for (size_t s = 0; s < B; s += 2 * half)
+                for (size_t j = 0; j < half; j++)
+                    bf_rows(f, base + (s + j) * w, base + (s + j + half) * w, w, tw[j * step], j == 0);
+        }
+    }
+    #pragma omp parallel for schedule(static)
+    for (size_t r = 0; r < B; r++) {
+        for (unsigned layer = mid; layer < lh; layer++) {
+            unsigned t = layer - mid;
+            size_t halfq = (size_t)1 << t, step = h >> (layer + 1);
+            for (size_t qs = 0; qs < nblk; qs += 2 * halfq)
+                for (size_t qj = 0; qj < halfq; qj++) {
+                    size_t i = (qs + qj) * B + r, j = qj * B + r;
+                    bf_rows(f, mat + i * w, mat + (i + (halfq << mid)) * w, w, tw[j * step], j == 0);
+                }
         }
     }
     free(tw);
@@ -223,6 +247,7 @@ void p3o_coset_lde_batch(int fi, const u32 *in, size_t h, size_t w, unsigned add
         memcpy(tmp, coeffs, h * w * 4);
         p3o_coset_dft_batch(fi, tmp, h, w, s);
         /* natural LDE index of (coset c, j) is j*nc + c */
+        #pragma omp parallel for schedule(static)
         for (size_t j = 0; j < h; j++) {
             size_t nat = j * nc + c;
             size_t row = bitrev_out ? bitrev(nat, lh + added_bits) : nat;

@@ -222,8 +222,8 @@ template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 //     copy per lane serialises into a 32-iteration R2UR/PLOP3 loop per warp: +25 % instructions, profiles/README.md);
 //   * all tiles of a pass have the same runtime width ct (16/20/24 columns; w = 100 -> 5 x 20) so that ONE launch covers
 //     every column and neighbouring tiles share DRAM bursts through L2.
-template <int F, int R_LOG, int CT_T, int THREADS>   // CT_T: compile-time tile width (16/20/24) or 0 = runtime a.ct
-__global__ void __launch_bounds__(THREADS, 1) ntt_pass_fast_kernel(const __grid_constant__ PassArgs a) {
+template <int F, int R_LOG, int CT_T, int THREADS, int NBUF>   // CT_T: compile-time tile width (16/20/24) or 0 = runtime a.ct
+__global__ void __launch_bounds__(THREADS, (NBUF == 1 && THREADS <= 256) ? 2 : 1) ntt_pass_fast_kernel(const __grid_constant__ PassArgs a) {
     constexpr int Q2 = (R_LOG + 1) / 2, Q1 = R_LOG - Q2;
     constexpr u32 E1 = 1u << Q1, E2 = 1u << Q2, R = 1u << R_LOG;
     const u32 CT = CT_T ? (u32)CT_T : a.ct;
@@ -232,7 +232,7 @@ __global__ void __launch_bounds__(THREADS, 1) ntt_pass_fast_kernel(const __grid_
     const u32 buf_words = (E1 * gstride + 3u) & ~3u;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     u32 *data0 = reinterpret_cast<u32 *>(smem_raw);
-    uint2 *tws0 = reinterpret_cast<uint2 *>(data0 + 2 * buf_words);
+    uint2 *tws0 = reinterpret_cast<uint2 *>(data0 + NBUF * buf_words);
 
     const int lowbits = a.log_n - a.l1;
     const int brsh = 32 - a.log_n;
@@ -269,7 +269,18 @@ __global__ void __launch_bounds__(THREADS, 1) ntt_pass_fast_kernel(const __grid_
         const u32 cpr = vec16 ? (cw >> 2) : cw;                  // chunks per row segment
         const u32 rs = (THREADS / cpr) & ~(E2 - 1u);             // rows per sweep: a multiple of E2 keeps the shared address linear
         const u32 nthr = rs * cpr;
-        if (threadIdx.x < nthr) {
+        if (rs == 0) {
+            // fewer than E2 whole rows per sweep (wide unaligned tiles): plain index arithmetic per chunk
+            for (u32 it = threadIdx.x; it < R * cpr; it += THREADS) {
+                const u32 rho = it / cpr, ch = it - rho * cpr;
+                const u32 e = vec16 ? 4u * ch : ch;
+                const u32 i = ibase | (rho << lowbits);
+                const u32 row = a.in_bitrev ? (__brev(i) >> brsh) : i;
+                u32 *dst = data + (rho >> Q2) * gstride + (rho & (E2 - 1u)) * CT + e;
+                const u32 *src = in + (size_t)row * a.w + e;
+                if (vec16) cp_async16(dst, src); else cp_async4(dst, src);
+            }
+        } else if (threadIdx.x < nthr) {
             const u32 rho0 = threadIdx.x / cpr, ch = threadIdx.x - rho0 * cpr;
             const u32 e = vec16 ? 4u * ch : ch;
             u32 *dst = data + (rho0 >> Q2) * gstride + (rho0 & (E2 - 1u)) * CT + e;
@@ -294,15 +305,20 @@ __global__ void __launch_bounds__(THREADS, 1) ntt_pass_fast_kernel(const __grid_
     u32 t = blockIdx.x;
     if (t >= total) return;
     if (shared_tw && a.n_cosets == 1) issue_twiddles(0, 0, tws0);   // once per CTA, lands with the first tile's group
-    issue(t, 0);
+    if (NBUF == 2) issue(t, 0);
     for (u32 k = 0; t < total; t += gridDim.x, k++) {
-        const u32 buf = k & 1u;
-        __syncthreads();   // every warp is done reading buffer buf^1 (tile k-1): it may be refilled
-        if (t + gridDim.x < total) { issue(t + gridDim.x, buf ^ 1u); cp_async_wait<1>(); }
-        else cp_async_wait<0>();
+        const u32 buf = NBUF == 2 ? (k & 1u) : 0u;
+        __syncthreads();   // every warp is done reading the buffer that is refilled next
+        if (NBUF == 2) {
+            if (t + gridDim.x < total) { issue(t + gridDim.x, buf ^ 1u); cp_async_wait<1>(); }
+            else cp_async_wait<0>();
+        } else {   // single buffer: other resident CTAs of this SM compute while this one waits for its tile
+            issue(t, 0);
+            cp_async_wait<0>();
+        }
         __syncthreads();
         u32 *data = data0 + buf * buf_words;
-        const uint2 *tws = (shared_tw && a.n_cosets == 1) ? tws0 : tws0 + buf * R;
+        const uint2 *tws = (shared_tw && a.n_cosets == 1) ? tws0 : tws0 + buf * R;  // NBUF == 1: buf == 0
         u32 coset, col, cw, T, ibase;
         decode(t, coset, col, cw, T, ibase);
         const u32 dg = THREADS / cw, dc = THREADS - dg * cw;
@@ -453,21 +469,22 @@ static int32_t launch_pass_ct(p3gpu_ctx *ctx, const PassArgs &a) {
     return P3GPU_OK;
 }
 
-template <int F, int R_LOG, int CT_T, int THREADS>
+template <int F, int R_LOG, int CT_T, int THREADS, int NBUF>
 static int32_t launch_fast_rct(p3gpu_ctx *ctx, const PassArgs &a) {
     constexpr int Q2 = (R_LOG + 1) / 2, Q1 = R_LOG - Q2;
     const u32 ct = a.ct;
     const u32 e2 = 1u << Q2, e1 = 1u << Q1;
     const u32 padw = (ct + 32u - ((e2 * ct) & 31u)) & 31u;
     const size_t buf_words = ((size_t)e1 * (e2 * ct + padw) + 3) & ~(size_t)3;
-    const size_t smem = 2 * buf_words * 4 + 2 * ((size_t)1 << R_LOG) * sizeof(uint2);
-    auto kern = ntt_pass_fast_kernel<F, R_LOG, CT_T, THREADS>;
+    const size_t smem = NBUF * buf_words * 4 + NBUF * ((size_t)1 << R_LOG) * sizeof(uint2);
+    auto kern = ntt_pass_fast_kernel<F, R_LOG, CT_T, THREADS, NBUF>;
     P3_CHECK(smem <= 227 * 1024, P3GPU_EINVAL, "ntt: tile does not fit shared memory");
     if (smem > 48 * 1024) P3_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const size_t tiles = ((size_t)1 << (a.log_n - R_LOG)) * a.n_ctiles * a.n_cosets;
     P3_CHECK(tiles < (1ull << 31), P3GPU_EINVAL, "ntt: grid too large");
     // persistent grid: one CTA per SM (more when the tile is small enough for several to be resident)
-    size_t per_sm = std::min<size_t>(2, (227 * 1024) / (smem + 1024));
+    size_t per_sm = std::min<size_t>(NBUF == 1 ? 2048 / THREADS : 2, (227 * 1024) / (smem + 1024));
+    if (THREADS * per_sm * 80 > 65536) per_sm = 65536 / (THREADS * 80);   // register file: ~80 registers per thread
     if (per_sm < 1) per_sm = 1;
     const size_t grid = std::min(tiles, per_sm * (size_t)ctx->sm_count);
     kern<<<(unsigned)grid, THREADS, smem, ctx->stream>>>(a);
@@ -477,9 +494,9 @@ static int32_t launch_fast_rct(p3gpu_ctx *ctx, const PassArgs &a) {
 }
 template <int F, int R_LOG, int CT_T>
 static int32_t launch_fast_rc(p3gpu_ctx *ctx, const PassArgs &a) {
-    static const int threads = env_int("P3GPU_NTT_THREADS", 512);
-    if (threads == 768) return launch_fast_rct<F, R_LOG, CT_T, 768>(ctx, a);
-    return launch_fast_rct<F, R_LOG, CT_T, 512>(ctx, a);
+    static const int threads = env_int("P3GPU_NTT_THREADS", 256);
+    if (threads == 256) return launch_fast_rct<F, R_LOG, CT_T, 256, 1>(ctx, a);   // 2-3 single-buffered CTAs per SM
+    return launch_fast_rct<F, R_LOG, CT_T, 512, 2>(ctx, a);                       // 1 double-buffered CTA per SM
 }
 template <int F, int R_LOG>
 static int32_t launch_fast_r(p3gpu_ctx *ctx, const PassArgs &a) {

@@ -58,7 +58,8 @@ def test_config1_forward_ntt_babybear_2_16(gpu):
 
 
 @pytest.mark.parametrize("f", FIELDS, ids=lambda f: f.name)
-@pytest.mark.parametrize("log_h,w", [(0, 3), (1, 1), (2, 5), (3, 17), (5, 4), (7, 33), (9, 100), (10, 7), (11, 36), (12, 3), (13, 20), (15, 2)])
+@pytest.mark.parametrize("log_h,w", [(0, 3), (1, 1), (2, 5), (3, 17), (5, 4), (7, 33), (9, 100), (10, 7), (11, 36), (12, 3), (13, 20), (15, 2),
+                                     (10, 33), (10, 45), (9, 21), (8, 24), (10, 25), (7, 48), (10, 52)])
 def test_dft_family_matches_oracle(gpu, f, log_h, w):
     # dft/tests/testing.rs:298-378: dft / idft / coset_dft / coset_idft agree with the definition for many shapes
     dft = Radix2DitParallel(f, gpu)
@@ -82,7 +83,7 @@ def test_small_dft_vs_naive_definition(gpu, f):
 
 
 @pytest.mark.parametrize("f", FIELDS, ids=lambda f: f.name)
-@pytest.mark.parametrize("log_h,w,added_bits", [(0, 2, 1), (1, 3, 2), (4, 5, 0), (4, 5, 1), (6, 9, 3), (10, 100, 1), (12, 37, 1), (13, 8, 2), (14, 4, 1)])
+@pytest.mark.parametrize("log_h,w,added_bits", [(0, 2, 1), (1, 3, 2), (4, 5, 0), (4, 5, 1), (6, 9, 3), (10, 100, 1), (12, 37, 1), (13, 8, 2), (14, 4, 1), (10, 33, 1), (9, 45, 2)])
 def test_coset_lde_matches_oracle(gpu, f, log_h, w, added_bits):
     # traits.rs:227-259 + radix_2_dit_parallel.rs:181-246: values AND memory layout (bit-reversed rows)
     dft = Radix2DitParallel(f, gpu)
