@@ -223,7 +223,7 @@ template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 //   * all tiles of a pass have the same runtime width ct (16/20/24 columns; w = 100 -> 5 x 20) so that ONE launch covers
 //     every column and neighbouring tiles share DRAM bursts through L2.
 template <int F, int R_LOG, int CT_T, int THREADS, int NBUF>   // CT_T: compile-time tile width (16/20/24) or 0 = runtime a.ct
-__global__ void __launch_bounds__(THREADS, (NBUF == 1 && THREADS <= 256) ? 2 : 1) ntt_pass_fast_kernel(const __grid_constant__ PassArgs a) {
+__global__ void __launch_bounds__(THREADS, (NBUF == 1 && THREADS <= 384) ? 2 : 1) ntt_pass_fast_kernel(const __grid_constant__ PassArgs a) {
     constexpr int Q2 = (R_LOG + 1) / 2, Q1 = R_LOG - Q2;
     constexpr u32 E1 = 1u << Q1, E2 = 1u << Q2, R = 1u << R_LOG;
     const u32 CT = CT_T ? (u32)CT_T : a.ct;
@@ -495,8 +495,11 @@ static int32_t launch_fast_rct(p3gpu_ctx *ctx, const PassArgs &a) {
 template <int F, int R_LOG, int CT_T>
 static int32_t launch_fast_rc(p3gpu_ctx *ctx, const PassArgs &a) {
     static const int threads = env_int("P3GPU_NTT_THREADS", 256);
-    if (threads == 256) return launch_fast_rct<F, R_LOG, CT_T, 256, 1>(ctx, a);   // 2-3 single-buffered CTAs per SM
-    return launch_fast_rct<F, R_LOG, CT_T, 512, 2>(ctx, a);                       // 1 double-buffered CTA per SM
+    if (threads == 512) return launch_fast_rct<F, R_LOG, CT_T, 512, 2>(ctx, a);   // 1 double-buffered CTA per SM
+    // default: 2 single-buffered 256-thread CTAs per SM (one loads its tile while the other computes).  Measured on the
+    // 2^20 x 100 LDE: 1.82 ms, vs 2.17 ms for 1 x 512 double-buffered; block sizes 128/192/320/384 give 1.88/1.82/1.91/1.92 ms —
+    // the kernel is bound by the integer pipes (profiles/README.md), not by the number of resident warps.
+    return launch_fast_rct<F, R_LOG, CT_T, 256, 1>(ctx, a);
 }
 template <int F, int R_LOG>
 static int32_t launch_fast_r(p3gpu_ctx *ctx, const PassArgs &a) {
