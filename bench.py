@@ -12,8 +12,9 @@ output.  A "step" is one LDE of one synthetic matrix (uniform field elements, se
   roofline    HBM roofline of the NTT pass kernel: algorithmic bytes of one LDE (read input once + write output once,
               SURVEY.md §8d: 1,258,291,200 B) / device time of the step (all launches of a step are the same kernel).
   cpu_baseline the oracle port (OpenMP C restatement, oracle/p3_oracle.c) on the host cores, bounded sample.
-  others      (N=1 only) the remaining single-GPU BASELINE configs timed the same way (Merkle config 3, Keccak commit
-              config 4 shape scaled to fit the time budget is reported at its own size, FRI commit phase).
+  others      (N=1 only) the remaining single-GPU BASELINE configs timed the same way: config 3 (Poseidon2 Merkle 2^22 x 100),
+              config 4 (BabyBear 2^22 x 300 LDE + Keccak Merkle, FRI commit phase 2^23) and the config 5 hot path
+              (KoalaBear 2^20 x 1312 trace commit + quotient commit + FRI commit phase, all device resident).
 
 --impl reference: times the reference's CPU algorithm (the oracle port — the reference is Rust and cannot be built in this
 image) on the same metric; rank 0 only under torchrun.
@@ -50,12 +51,33 @@ def parse():
 
 # ------------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
+    """Samples SM clock + throttle reasons DURING the timed region (NVML, ~1 kHz; falls back to nvidia-smi)."""
+
     def __init__(self, idx=0):
         self.idx, self.samples, self.reasons, self.stop = idx, [], set(), False
         self.max_mhz = None
         self.t = threading.Thread(target=self.run, daemon=True)
 
     def run(self):
+        try:
+            import pynvml as N
+            N.nvmlInit()
+            h = N.nvmlDeviceGetHandleByIndex(self.idx)
+            self.max_mhz = float(N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM))
+            bits = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20}
+            while not self.stop:
+                self.samples.append(float(N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)))
+                try:
+                    r = N.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    r = N.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for n, b in bits.items():
+                    if r & b:
+                        self.reasons.add(n)
+                time.sleep(0.001)
+            return
+        except Exception:
+            pass
         q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
@@ -69,9 +91,8 @@ class ClockSampler:
                         self.reasons.add(n)
             except Exception:
                 pass
-            time.sleep(0.1)
 
-    def __enter__(self): self.t.start(); return self
+    def __enter__(self): self.t.start(); time.sleep(0.05); self.samples.clear(); return self
     def __exit__(self, *a): self.stop = True; self.t.join(timeout=6)
 
     def summary(self):
@@ -104,7 +125,7 @@ def run_reference(args):
     O.build(native=True)
     cores = os.cpu_count() or 1
     f = 1
-    cols = 8
+    cols = W if cores >= 16 else 16          # full workload on a many-core host, a 16-column sample on small hosts
     m = O.random_matrix(f, 1 << LOG_H, cols, seed=1)
     for _ in range(min(args.warmup, 1)):
         O.coset_lde_batch(f, m, ADDED_BITS, O.generator(f))
@@ -220,14 +241,14 @@ def main():
     else:
         peak, peak_src = 6650.0, "B200_PROFILING.md fallback (of fallback)"
     achieved = ALG_BYTES / (ms * 1e-3) / 1e9
-    traffic = None
+    traffic = None          # dram__bytes_read.sum + dram__bytes_write.sum summed over the launches of one LDE step (ncu --set full)
     tp = ROOT / "profiles" / "ncu_traffic.json"
     if tp.exists():
         traffic = json.loads(tp.read_text()).get("lde_step_dram_bytes")
-    line["roofline"] = {"bound": "hbm", "kernel": "ntt_pass_kernel (all launches of an LDE step)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    line["roofline"] = {"bound": "hbm", "kernel": "ntt_pass_fast_kernel (all launches of an LDE step)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                         "algorithmic_bytes_per_step": ALG_BYTES, "launches_per_step": launches / args.steps,
-                        "note": "kernel is integer-issue bound (3 IMAD + 6 ALU per butterfly, 3.146e9 butterflies): see DESIGN.md"}
+                        "note": "integer-pipe bound, not HBM bound: 3.146e9 butterflies x (IMAD.HI + 2 IMAD + 4 ALU); register-only butterfly loop peaks at 12.85/clk/SM = 0.86 ms floor (DESIGN.md 4.1)"}
 
     # ---- secondary workloads (single GPU only)
     if world == 1 and not args.no_others:
@@ -244,17 +265,41 @@ def main():
         t, nl = timed(lambda: gpu.merkle_commit(KB.id, _lib.HASH_POSEIDON2_W24, [xw]), k, 1)
         others["merkle_commit_poseidon2_w24_kb_2^21x328"] = {"ms": t, "Mperm_per_s": ((1 << 21) * 21 + (1 << 21) - 1) / t / 1e3}
         del xw
-        # config 4 shape at 1/4 scale: BabyBear 2^20 x 300, LDE blowup 2 + Keccak Merkle (cap 3) + FRI commit phase on 2^21 EF4
-        xb = torch.randint(0, BB.P, (1 << 20, 300), device=dev, dtype=torch.int32, generator=g)
-        t, nl = timed(lambda: gpu.pcs_commit(BB.id, _lib.HASH_KECCAK, xb, 1), k, 1)
-        others["pcs_commit_keccak_bb_2^20x300"] = {"ms": t, "launches": nl / k}
+        # config 4 (full size): BabyBear 2^22 x 300, TwoAdicFriPcs::commit = LDE blowup 2 + Keccak Merkle, then the FRI
+        # commit phase on a 2^23 EF4 codeword with fixed betas (arities [3]*7+[1], cap_height 3)
+        betas = np.random.default_rng(2).integers(0, BB.P, size=(10, 4), dtype=np.uint32)
+        xb = torch.randint(0, BB.P, (1 << 22, 300), device=dev, dtype=torch.int32, generator=g)
+        t, nl = timed(lambda: gpu.pcs_commit(BB.id, _lib.HASH_KECCAK, xb, 1), 2, 1)
+        others["config4_pcs_commit_keccak_bb_2^22x300"] = {"ms": t, "launches": nl / 2, "lde_out_Gelem_per_s": (1 << 23) * 300 / t / 1e6}
         del xb
-        betas = np.random.default_rng(2).integers(0, BB.P, size=(8, 4), dtype=np.uint32)
-        v0 = torch.randint(0, BB.P, (1 << 21, 4), device=dev, dtype=torch.int32, generator=g)
-        def fri():
+        v0 = torch.randint(0, BB.P, (1 << 23, 4), device=dev, dtype=torch.int32, generator=g)
+        def fri4():
             gpu.fri_commit_phase(BB.id, _lib.HASH_KECCAK, v0.clone(), 1, 0, 3, 3, betas)
-        t, nl = timed(fri, k, 1)
-        others["fri_commit_phase_keccak_bb_2^21"] = {"ms": t, "launches": nl / k}
+        t, nl = timed(fri4, k, 1)
+        others["config4_fri_commit_phase_keccak_bb_2^23"] = {"ms": t, "launches": nl / k}
+        del v0
+        # config 5 hot path (prover.rs:215,319,394 minus the host-side AIR/quotient/opening work): KoalaBear, trace 2^20 x 1312,
+        # blowup 2, Poseidon2-24 sponge + Poseidon2-16 compression, cap 3; quotient commit 2 x (2^20 x 4); FRI commit phase 2^21
+        xt = torch.randint(0, KB.P, (1 << 20, 1312), device=dev, dtype=torch.int32, generator=g)
+        t_trace, nl = timed(lambda: gpu.pcs_commit(KB.id, _lib.HASH_POSEIDON2_W24, xt, 1), 2, 1)
+        tl, _ = timed(lambda: gpu.coset_lde_batch(KB.id, xt, 1, KB.generator), 2, 1)
+        del xt
+        xq = torch.randint(0, KB.P, (1 << 20, 4), device=dev, dtype=torch.int32, generator=g)
+        def quot():
+            a_ = gpu.coset_lde_batch(KB.id, xq, 1, KB.generator); b_ = gpu.coset_lde_batch(KB.id, xq, 1, KB.generator)
+            gpu.merkle_commit(KB.id, _lib.HASH_POSEIDON2_W24, [a_, b_])
+        t_quot, _ = timed(quot, k, 1)
+        v1 = torch.randint(0, KB.P, (1 << 21, 4), device=dev, dtype=torch.int32, generator=g)
+        kbetas = np.random.default_rng(3).integers(0, KB.P, size=(10, 4), dtype=np.uint32)
+        def fri5():
+            gpu.fri_commit_phase(KB.id, _lib.HASH_POSEIDON2_W24, v1.clone(), 1, 0, 3, 3, kbetas)
+        t_fri, _ = timed(fri5, k, 1)
+        others["config5_hot_path_kb_2^20x1312"] = {
+            "commit_trace_ms": t_trace, "of_which_lde_ms": tl, "commit_quotient_ms": t_quot, "fri_commit_phase_ms": t_fri,
+            "hot_path_total_ms": t_trace + t_quot + t_fri,
+            "note": "device-resident LDE+Merkle+FRI of prove_prime_field_31 -f koala-bear -o poseidon-2-permutations -l 20; "
+                    "AIR quotient evaluation and openings are host-side in the reference and out of scope (SURVEY 8f)"}
+        del v1, xq
         line["others"] = others
 
     # ---- CPU baseline (rank 0, N=1)

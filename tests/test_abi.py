@@ -68,3 +68,17 @@ def test_arity_schedule():
         compute_log_arity_for_round(5, None, 1, 0)
     p = FriParameters.new_benchmark_high_arity(None)
     assert (p.log_blowup, p.max_log_arity, p.num_queries, p.query_proof_of_work_bits) == (1, 3, 100, 16)
+
+
+def test_cpp_host_mirror_compiles_and_fails_loudly_without_gpu(tmp_path):
+    """include/p3gpu.hpp (C++ mirror of the trait surfaces) compiles against the header and links libp3gpu.so."""
+    import subprocess
+    exe = tmp_path / "host_mirror_check"
+    lib_dir = ROOT / "plonky3_b200"
+    subprocess.run(["/usr/bin/g++", "-std=c++17", "-O1", "-I", str(ROOT / "include"), str(ROOT / "tests" / "cpp" / "host_mirror_check.cpp"),
+                    "-o", str(exe), f"-L{lib_dir}", "-l:libp3gpu.so", f"-Wl,-rpath,{lib_dir}"], check=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    if torch.cuda.is_available():
+        assert r.returncode == 0, r.stdout + r.stderr
+    else:
+        assert r.returncode == 3 and "no CPU fallback" in r.stdout, r.stdout + r.stderr
