@@ -138,6 +138,10 @@ int32_t p3gpu_fri_fold_dev(p3gpu_ctx *ctx, int field, const uint32_t *d_in, size
 int32_t p3gpu_fri_fold(p3gpu_ctx *ctx, int field, const uint32_t *h_in, size_t rows, unsigned log_arity,
                        const uint32_t beta[4], uint32_t *h_out);
 
+/* acc[i] += s * x[i] over EF4 (n elements, device memory): the roll-in of a shorter FRI input, folded += beta^arity * input
+ * (fri/src/prover.rs:258-265). */
+int32_t p3gpu_ef_axpy_dev(p3gpu_ctx *ctx, int field, uint32_t *d_acc, const uint32_t *d_x, size_t n, const uint32_t s[4]);
+
 /* commit_phase (fri/src/prover.rs:192-286) for ONE input vector with caller-supplied betas (the Fiat-Shamir
  * transcript stays on the host; with commit_proof_of_work_bits = 0 a round's beta depends only on that round's cap,
  * so a host driving the transcript calls p3gpu_merkle_commit_dev / p3gpu_fri_fold_dev per round instead).

@@ -286,20 +286,34 @@ def compute_log_arity_for_round(log_cur, next_input_log, log_final, max_log_arit
     return min(m, max_log_arity)
 
 
-def commit_phase(f, hs: Hasher, cap_height, folded, log_blowup, log_final_poly_len, max_log_arity, betas):
-    """FRI commit phase with externally supplied betas (fri/src/prover.rs:192-286, single input vector,
-    no proof-of-work: commit_proof_of_work_bits = 0 as in the benchmark parameters).  Returns
+def commit_phase(f, hs: Hasher, cap_height, inputs, log_blowup, log_final_poly_len, max_log_arity, betas):
+    """FRI commit phase with externally supplied betas (fri/src/prover.rs:192-286; no proof-of-work:
+    commit_proof_of_work_bits = 0 as in the benchmark parameters).  `inputs`: one (len,4) EF4 vector or a list of them in
+    descending length (shorter inputs are rolled in with beta^arity, prover.rs:258-265).  Returns
     (list of caps, list of log_arities, final folded vector before the final-poly iDFT)."""
-    folded = _u32(folded)
+    if isinstance(inputs, np.ndarray):
+        inputs = [inputs]
+    inputs = [_u32(v) for v in inputs]
+    folded = inputs.pop(0)
     caps, arities = [], []
     log_final = log_blowup + log_final_poly_len
     k = 0
     while folded.shape[0] > (1 << log_final):
         log_cur = int(np.log2(folded.shape[0]))
-        la = compute_log_arity_for_round(log_cur, None, log_final, max_log_arity)
+        nxt = int(np.log2(inputs[0].shape[0])) if inputs else None
+        la = compute_log_arity_for_round(log_cur, nxt, log_final, max_log_arity)
         arities.append(la)
         leaves = folded.reshape(folded.shape[0] >> la, (1 << la) * 4)   # ExtensionMmcs flattening
         layers = merkle_tree(hs, [leaves])
         caps.append(merkle_cap(layers, cap_height))
-        folded = fold_matrix(f, folded, la, betas[k]); k += 1
+        beta = _u32(betas[k]); k += 1
+        folded = fold_matrix(f, folded, la, beta)
+        if inputs and inputs[0].shape[0] == folded.shape[0]:
+            bp = beta
+            for _ in range(la):
+                bp = ef_mul(f, bp, bp)
+            x = inputs.pop(0)
+            for i in range(folded.shape[0]):
+                t = ef_mul(f, bp, x[i])
+                folded[i] = [add(f, int(a), int(b)) for a, b in zip(folded[i], t)]
     return caps, arities, folded

@@ -272,6 +272,11 @@ int32_t p3gpu_fri_fold(p3gpu_ctx *ctx, int field, const uint32_t *h_in, size_t r
     return P3GPU_OK;
 }
 
+int32_t p3gpu_ef_axpy_dev(p3gpu_ctx *ctx, int field, uint32_t *d_acc, const uint32_t *d_x, size_t n, const uint32_t s[4]) {
+    P3_CHECK(ctx && d_acc && d_x && s, P3GPU_EINVAL, "null argument");
+    return fri_ef_axpy(ctx, field, d_acc, d_x, n, s);
+}
+
 // fri/src/config.rs:180-207 with a single input vector (next_input_log_height = None)
 static unsigned log_arity_for_round(unsigned log_cur, unsigned log_final, unsigned max_log_arity) {
     const unsigned m = log_cur - log_final;

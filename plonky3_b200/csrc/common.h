@@ -101,6 +101,8 @@ int32_t hash_merkle_from_digests(p3gpu_ctx *ctx, int field, int hash, const u32 
 // fri.cu
 int32_t fri_fold(p3gpu_ctx *ctx, int field, const u32 *d_in, size_t rows, unsigned log_arity, const u32 beta[4], u32 *d_out);
 
+int32_t fri_ef_axpy(p3gpu_ctx *ctx, int field, u32 *d_acc, const u32 *d_x, size_t n, const u32 s[4]);
+
 static inline unsigned log2_floor(size_t x) { unsigned l = 0; while ((x >> l) > 1) l++; return l; }
 static inline bool is_pow2(size_t x) { return x && !(x & (x - 1)); }
 

@@ -58,6 +58,16 @@ __global__ void __launch_bounds__(128) fri_fold_kernel(const u32 *in, u32 *out, 
     *reinterpret_cast<uint4 *>(out + row * 4) = make_uint4(v[0].c[0], v[0].c[1], v[0].c[2], v[0].c[3]);
 }
 
+// folded[i] += s * x[i] over EF4 (commit_phase roll-in of a shorter input, fri/src/prover.rs:258-265: s = beta^arity)
+template <int F> __global__ void __launch_bounds__(256) ef_axpy_kernel(u32 *acc, const u32 *x, size_t n, const Ef4<F> s) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint4 a = reinterpret_cast<const uint4 *>(acc)[i], b = __ldg(reinterpret_cast<const uint4 *>(x) + i);
+    Ef4<F> xv; xv.c[0] = b.x; xv.c[1] = b.y; xv.c[2] = b.z; xv.c[3] = b.w;
+    const Ef4<F> p = ef_mul<F>(s, xv);
+    reinterpret_cast<uint4 *>(acc)[i] = make_uint4(fp_add<F>(a.x, p.c[0]), fp_add<F>(a.y, p.c[1]), fp_add<F>(a.z, p.c[2]), fp_add<F>(a.w, p.c[3]));
+}
+
 template <int F> static int32_t ensure_fold_table(p3gpu_ctx *ctx, size_t len) {
     if (ctx->fold_table_len[F] >= len) return P3GPU_OK;
     size_t cap = 1;
@@ -106,6 +116,17 @@ int32_t fri_fold(p3gpu_ctx *ctx, int field, const u32 *d_in, size_t rows, unsign
     P3_CHECK(log2_floor(rows) + log_arity <= adicity, P3GPU_EINVAL, "fold: vector longer than the two-adic subgroup");
     return field == BABY_BEAR ? fold_impl<BABY_BEAR>(ctx, d_in, rows, log_arity, beta, d_out)
                               : fold_impl<KOALA_BEAR>(ctx, d_in, rows, log_arity, beta, d_out);
+}
+
+int32_t fri_ef_axpy(p3gpu_ctx *ctx, int field, u32 *d_acc, const u32 *d_x, size_t n, const u32 s[4]) {
+    P3_CHECK(field == BABY_BEAR || field == KOALA_BEAR, P3GPU_EUNSUPPORTED, "unknown field %d", field);
+    if (n == 0) return P3GPU_OK;
+    const unsigned g = (unsigned)((n + 255) / 256);
+    if (field == BABY_BEAR) { Ef4<BABY_BEAR> v; for (int k = 0; k < 4; k++) v.c[k] = s[k]; ef_axpy_kernel<BABY_BEAR><<<g, 256, 0, ctx->stream>>>(d_acc, d_x, n, v); }
+    else { Ef4<KOALA_BEAR> v; for (int k = 0; k < 4; k++) v.c[k] = s[k]; ef_axpy_kernel<KOALA_BEAR><<<g, 256, 0, ctx->stream>>>(d_acc, d_x, n, v); }
+    ctx->launches++;
+    P3_CUDA(cudaGetLastError());
+    return P3GPU_OK;
 }
 
 }  // namespace p3

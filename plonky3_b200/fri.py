@@ -99,8 +99,9 @@ def commit_phase(folding: TwoAdicFriFolding, params: FriParameters, inputs: list
         folded = folding.fold_matrix(beta, log_arity, leaves)
         data.append(prover_data)
         if inputs and inputs[0].shape[0] == folded.shape[0]:
-            # folded += beta^arity * input  (prover.rs:258-265); tiny host-side EF op kept on the host for generality
-            raise NotImplementedError("multiple FRI input heights: roll-in of shorter inputs is a §8(f) 'next' item")
+            # folded += beta^arity * input  (prover.rs:258-265)
+            beta_pow = _ef_exp_power_of_2(field, beta, log_arity)
+            folded = _ef_axpy(folding.gpu, field, folded, inputs.pop(0), beta_pow)
     fl = params.final_poly_len()
     final = folded[:fl]
     final = final.cpu().numpy().view(np.uint32) if _is_torch(final) else np.array(final, dtype=np.uint32)
@@ -108,6 +109,38 @@ def commit_phase(folding: TwoAdicFriFolding, params: FriParameters, inputs: list
         final = dft.idft_algebra_batch(reverse_matrix_index_bits(final.reshape(fl, 4)).reshape(fl, 1, 4)).reshape(fl, 4)
     challenger.observe_algebra_slice(final)
     return CommitPhaseResult(commits, data, log_arities, pow_witnesses, final)
+
+
+def _ef_mul_host(field: Field, a, b):
+    """EF4 product of two single elements on the host (binomial_extension.rs:724-770); scalar transcript arithmetic only."""
+    p = field.P
+    x = [field.from_monty(int(v)) for v in a]; y = [field.from_monty(int(v)) for v in b]
+    r = [0] * 7
+    for i in range(4):
+        for j in range(4):
+            r[i + j] = (r[i + j] + x[i] * y[j]) % p
+    out = [(r[i] + field.EXT_W * r[i + 4]) % p for i in range(3)] + [r[3]]
+    return np.array([field.to_monty(v) for v in out], dtype=np.uint32)
+
+
+def _ef_exp_power_of_2(field: Field, a, k: int):
+    for _ in range(k):
+        a = _ef_mul_host(field, a, a)
+    return np.asarray(a, dtype=np.uint32)
+
+
+def _ef_axpy(gpu, field: Field, acc, x, s):
+    import torch
+    to_dev = lambda t: t if _is_torch(t) else torch.from_numpy(np.ascontiguousarray(t, dtype=np.uint32).view(np.int32)).to(f"cuda:{gpu.device}")
+    was_host = not _is_torch(acc)
+    out = gpu.ef_axpy(field.id, to_dev(acc).contiguous(), to_dev(x).contiguous(), s)
+    return out.cpu().numpy().view(np.uint32) if was_host else out
+
+
+def split_evals(num_chunks: int, evals):
+    """TwoAdicMultiplicativeCoset::split_evals (commit/src/domain.rs:257-290): chunk c takes rows c, c+num_chunks, ..."""
+    _log2_strict(num_chunks)
+    return [evals[c::num_chunks].contiguous() if _is_torch(evals) else np.ascontiguousarray(evals[c::num_chunks]) for c in range(num_chunks)]
 
 
 class TwoAdicFriPcs:
@@ -128,6 +161,23 @@ class TwoAdicFriPcs:
             shift = f.div(f.generator, dshift)                   # two_adic_pcs.rs:312
             ldes.append(self.dft.coset_lde_batch(evals, self.fri.log_blowup, shift).bit_reverse_rows())
         return self.mmcs.commit(ldes)
+
+    def get_quotient_ldes(self, evaluations: list, num_chunks: int = 0):
+        """two_adic_pcs.rs:326-345: the same LDE as commit, without committing."""
+        f = self.dft.field
+        return [self.dft.coset_lde_batch(ev, self.fri.log_blowup, f.div(f.generator, dshift)).bit_reverse_rows()
+                for (dshift, log_size), ev in evaluations]
+
+    def commit_quotient(self, quotient_domain, quotient_evaluations, num_chunks: int):
+        """Pcs::commit_quotient default (commit/src/pcs/univariate.rs:98-119): split into num_chunks sub-cosets
+        shift * h^i * K (domain.rs:243-255), LDE each, commit the batch."""
+        f = self.dft.field
+        shift, log_size = quotient_domain
+        log_chunks = _log2_strict(num_chunks)
+        h = f.two_adic_generator(log_size)
+        subs = split_evals(num_chunks, quotient_evaluations)
+        doms = [(f.mul(shift, f.pow(h, i)), log_size - log_chunks) for i in range(num_chunks)]
+        return self.commit_ldes(self.get_quotient_ldes(list(zip(doms, subs)), num_chunks))
 
     def commit_ldes(self, ldes: list):
         min_height = 1 << self.fri.log_blowup

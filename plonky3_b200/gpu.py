@@ -177,6 +177,14 @@ class Gpu:
         check(self.L.p3gpu_fri_fold(self.h, field, v.ctypes.data, rows, log_arity, b.ctypes.data, out.ctypes.data))
         return out
 
+    def ef_axpy(self, field, acc_dev, x_dev, s):
+        """acc += s * x over EF4, in place on the device (commit_phase roll-in, prover.rs:258-265)."""
+        a, x = self._dev(acc_dev), self._dev(x_dev); self._use_torch_stream()
+        sv = np.ascontiguousarray(s, dtype=np.uint32)
+        assert a.numel() == x.numel() and sv.size == 4
+        check(self.L.p3gpu_ef_axpy_dev(self.h, field, a.data_ptr(), x.data_ptr(), a.numel() // 4, sv.ctypes.data))
+        return a
+
     def fri_commit_phase(self, field, hash_kind, vec_ef_dev, log_blowup, log_final_poly_len, max_log_arity, cap_height, betas):
         """All commit-phase rounds on the device with caller-supplied betas.  vec_ef_dev (CUDA, consumed).
         Returns (caps: list of (n,8) arrays, log_arities, final (len,4) array)."""

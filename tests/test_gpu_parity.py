@@ -241,6 +241,40 @@ def test_commit_phase_matches_oracle(gpu, kind, f):
     assert las == oar and all(np.array_equal(a, b) for a, b in zip(caps, ocaps)) and np.array_equal(final, ofinal)
 
 
+def test_commit_phase_with_two_input_heights(gpu):
+    # fri/src/prover.rs:258-265: a shorter input is rolled in as folded += beta^arity * input; the arity schedule stops at
+    # the next input's height (config.rs:180-207)
+    f = KoalaBear
+    mmcs, ohs = _mmcs_pair(f, "p2w16", gpu, cap_height=1)
+    params = FriParameters.new_benchmark_high_arity(mmcs)
+    v0, v1 = O.random_matrix(f.id, 1 << 10, 4, seed=1), O.random_matrix(f.id, 1 << 8, 4, seed=2)
+    betas = O.random_matrix(f.id, 8, 4, seed=3)
+    ocaps, oar, ofinal = O.commit_phase(f.id, ohs, 1, [v0, v1], 1, 0, 3, betas)
+    assert oar[0] == 2
+    ch = FixedBetaChallenger(betas)
+    res = commit_phase(TwoAdicFriFolding(f, gpu), params, [dev(v0), dev(v1)], ch, Radix2DitParallel(f, gpu))
+    assert res.log_arities == oar
+    assert all(np.array_equal(a, b) for a, b in zip(res.commits, ocaps))
+    assert np.array_equal(res.final_poly, ofinal[:1])
+
+
+def test_commit_quotient_matches_oracle(gpu):
+    # Pcs::commit_quotient (commit/src/pcs/univariate.rs:98-119): split_evals -> sub-coset LDEs -> one batch commitment
+    f = KoalaBear
+    mmcs, ohs = _mmcs_pair(f, "p2w24", gpu, cap_height=0)
+    pcs = TwoAdicFriPcs(Radix2DitParallel(f, gpu), mmcs, FriParameters.new_benchmark_high_arity(mmcs))
+    log_n, chunks = 9, 2
+    q = O.random_matrix(f.id, 1 << log_n, 4, seed=4)                    # evaluations over GENERATOR * H, natural order
+    cap, tree = pcs.commit_quotient((f.generator, log_n), q, chunks)
+    h = O.two_adic_generator(f.id, log_n)
+    ldes = []
+    for i in range(chunks):
+        sub = np.ascontiguousarray(q[i::chunks])
+        dshift = O.mul(f.id, f.generator, O.fpow(f.id, h, i))
+        ldes.append(O.coset_lde_batch(f.id, sub, 1, O.mul(f.id, f.generator, O.inv(f.id, dshift)), bitrev_out=True))
+    assert np.array_equal(cap, O.merkle_cap(O.merkle_tree(ohs, ldes), 0))
+
+
 def test_pcs_commit_matches_oracle(gpu):
     # TwoAdicFriPcs::commit (two_adic_pcs.rs:300-324): LDE onto GENERATOR*K, bit-reversed, Poseidon2 MMCS
     f = KoalaBear
