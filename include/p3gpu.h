@@ -154,6 +154,24 @@ int32_t p3gpu_fri_commit_phase_dev(p3gpu_ctx *ctx, int field, int hash, uint32_t
                                    uint32_t *h_caps, size_t *cap_lens, unsigned *log_arities, size_t *n_rounds,
                                    uint32_t *h_final);
 
+/* ---- Pcs::open, pre-FRI part (fri/src/two_adic_pcs.rs:413-662) ---------------- */
+/* compute_inverse_denominators (:743-780): d_inv_denoms[i] = 1/(z - x_i) for x_i = GENERATOR * w^bitrev(i), i < 2^log_height
+ * (EF4, bit-reversed coset order, so a prefix serves every smaller height).  If d_adjusted != NULL it receives
+ * 1/(z - x_i) - 1/z (compute_adjusted_weights) and zinv = 1/z must be supplied. */
+int32_t p3gpu_open_inv_denoms_dev(p3gpu_ctx *ctx, int field, unsigned log_height, const uint32_t z[4], const uint32_t *zinv,
+                                  uint32_t *d_inv_denoms, uint32_t *d_adjusted);
+/* Matrix::columnwise_dot_product: d_out[j] = scale * sum_i mat[i][j] * vec[i]  (vec: h EF4 values, out: w EF4 values; scale may be
+ * NULL).  With vec = adjusted weights and scale = z (z^N - g^N) / (N g^N) this is interpolate_coset_with_precomputation
+ * (matrix/src/interpolation.rs:161-193) on the first h rows of a committed bit-reversed LDE. */
+int32_t p3gpu_columnwise_dot_dev(p3gpu_ctx *ctx, int field, const uint32_t *d_mat, size_t h, size_t w, const uint32_t *d_vec_ef,
+                                 const uint32_t *scale, uint32_t *d_out);
+/* rowwise_packed_dot_product with the powers of alpha (:622-626): d_out[i] = sum_j alpha^j * mat[i][j]  (h EF4 values). */
+int32_t p3gpu_rowwise_dot_dev(p3gpu_ctx *ctx, int field, const uint32_t *d_mat, size_t h, size_t w, const uint32_t alpha[4],
+                              uint32_t *d_out);
+/* reduced-opening accumulation (:640-657): d_ro[i] += coeff * (yred - d_r[i]) * d_inv_denoms[i], i < h. */
+int32_t p3gpu_open_reduce_dev(p3gpu_ctx *ctx, int field, uint32_t *d_ro, const uint32_t *d_r, const uint32_t *d_inv_denoms, size_t h,
+                              const uint32_t coeff[4], const uint32_t yred[4]);
+
 /* ---- Pcs::commit ------------------------------------------------------------------------------ */
 /* TwoAdicFriPcs::commit for one matrix whose domain is the subgroup H (shift = GENERATOR / 1):
  * LDE onto GENERATOR*K with K = |H| << log_blowup, bit-reversed rows, then MerkleTreeMmcs::commit.

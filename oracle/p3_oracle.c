@@ -597,3 +597,79 @@ void p3o_fold_matrix(int fi, const u32 *in, size_t rows, unsigned log_arity, con
     memcpy(out, data, rows * 16);
     free(data); free(nxt);
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * TwoAdicFriPcs::open — the pre-FRI device work:
+ *   compute_inverse_denominators   fri/src/two_adic_pcs.rs:743-780
+ *   columnwise_dot_product / interpolate_coset_with_precomputation   matrix/src/interpolation.rs:161-193
+ *   rowwise dot with powers of alpha + quotient accumulation          fri/src/two_adic_pcs.rs:622-657
+ * EF4 inverse through the Frobenius conjugates (any method gives the same canonical result).
+ * ---------------------------------------------------------------------------------------------- */
+static void ef_inv(const field_t *f, const u32 *a, u32 *out) {
+    /* zeta = W^((p-1)/4): phi(X) = zeta * X, zeta^2 = -1 */
+    u32 zeta = f_pow(f, f_to_monty(f, f->ext_w), ((u64)f->p - 1) / 4);
+    u32 a1z = f_mul(f, a[1], zeta), a3z = f_mul(f, a[3], zeta);
+    u32 c1[4] = {a[0], a1z, f_sub(f, 0, a[2]), f_sub(f, 0, a3z)};
+    u32 c2[4] = {a[0], f_sub(f, 0, a[1]), a[2], f_sub(f, 0, a[3])};
+    u32 c3[4] = {a[0], f_sub(f, 0, a1z), f_sub(f, 0, a[2]), a3z};
+    u32 b[4], n[4];
+    ef_mul(f, c1, c2, b); ef_mul(f, b, c3, b);
+    ef_mul(f, a, b, n);            /* norm: lies in the base field (n[1..3] == 0) */
+    u32 ninv = f_inv(f, n[0]);
+    for (int k = 0; k < 4; k++) out[k] = f_mul(f, b[k], ninv);
+}
+void p3o_ef_inv(int fi, const u32 *a, u32 *out) { ef_inv(F(fi), a, out); }
+
+/* out[i] = 1 / (z - x_i), x_i = GENERATOR * w^bitrev(i), i < 2^log_h   (two_adic_pcs.rs:486-494, 743-780) */
+void p3o_open_inv_denoms(int fi, unsigned log_h, const u32 *z, u32 *out) {
+    const field_t *f = F(fi);
+    size_t h = (size_t)1 << log_h;
+    u32 g = f_to_monty(f, f->gen), w = f_two_adic_generator(f, log_h);
+    u32 *pts = (u32 *)malloc(h * 4);
+    pts[0] = g;
+    for (size_t i = 1; i < h; i++) pts[i] = f_mul(f, pts[i - 1], w);
+    #pragma omp parallel for schedule(static)
+    for (size_t i = 0; i < h; i++) {
+        u32 d[4] = {f_sub(f, z[0], pts[bitrev(i, log_h)]), z[1], z[2], z[3]};
+        ef_inv(f, d, out + 4 * i);
+    }
+    free(pts);
+}
+/* out[j] = sum_i mat[i][j] * v[i]   (v: h EF4 values; matrix/src/lib.rs columnwise_dot_product) */
+void p3o_columnwise_dot(int fi, const u32 *mat, size_t h, size_t w, const u32 *v, u32 *out) {
+    const field_t *f = F(fi);
+    #pragma omp parallel for schedule(static)
+    for (size_t j = 0; j < w; j++) {
+        u32 acc[4] = {0, 0, 0, 0};
+        for (size_t i = 0; i < h; i++)
+            for (int k = 0; k < 4; k++) acc[k] = f_add(f, acc[k], f_mul(f, mat[i * w + j], v[4 * i + k]));
+        memcpy(out + 4 * j, acc, 16);
+    }
+}
+/* out[i] = sum_j alpha^j * mat[i][j]   (rowwise_packed_dot_product with packed_ext_powers, two_adic_pcs.rs:622-626) */
+void p3o_rowwise_dot(int fi, const u32 *mat, size_t h, size_t w, const u32 *alpha, u32 *out) {
+    const field_t *f = F(fi);
+    u32 *pw = (u32 *)malloc(w * 16);
+    u32 cur[4] = {f_one(f), 0, 0, 0};
+    for (size_t j = 0; j < w; j++) { memcpy(pw + 4 * j, cur, 16); ef_mul(f, cur, alpha, cur); }
+    #pragma omp parallel for schedule(static)
+    for (size_t i = 0; i < h; i++) {
+        u32 acc[4] = {0, 0, 0, 0};
+        for (size_t j = 0; j < w; j++)
+            for (int k = 0; k < 4; k++) acc[k] = f_add(f, acc[k], f_mul(f, mat[i * w + j], pw[4 * j + k]));
+        memcpy(out + 4 * i, acc, 16);
+    }
+    free(pw);
+}
+/* ro[i] += coeff * (yred - r[i]) * inv_denom[i]   (two_adic_pcs.rs:640-657) */
+void p3o_open_reduce(int fi, u32 *ro, const u32 *r, const u32 *inv_denoms, size_t h, const u32 *coeff, const u32 *yred) {
+    const field_t *f = F(fi);
+    #pragma omp parallel for schedule(static)
+    for (size_t i = 0; i < h; i++) {
+        u32 d[4], t[4];
+        for (int k = 0; k < 4; k++) d[k] = f_sub(f, yred[k], r[4 * i + k]);
+        ef_mul(f, coeff, d, t);
+        ef_mul(f, t, inv_denoms + 4 * i, t);
+        for (int k = 0; k < 4; k++) ro[4 * i + k] = f_add(f, ro[4 * i + k], t[k]);
+    }
+}

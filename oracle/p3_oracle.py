@@ -72,6 +72,11 @@ def lib():
             ("p3o_merkle_total_digests", sz, [sz]),
             ("p3o_ef_mul", None, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
             ("p3o_fold_matrix", None, [C.c_int, C.c_void_p, sz, C.c_uint, C.c_void_p, C.c_void_p]),
+            ("p3o_ef_inv", None, [C.c_int, C.c_void_p, C.c_void_p]),
+            ("p3o_open_inv_denoms", None, [C.c_int, C.c_uint, C.c_void_p, C.c_void_p]),
+            ("p3o_columnwise_dot", None, [C.c_int, C.c_void_p, sz, sz, C.c_void_p, C.c_void_p]),
+            ("p3o_rowwise_dot", None, [C.c_int, C.c_void_p, sz, sz, C.c_void_p, C.c_void_p]),
+            ("p3o_open_reduce", None, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, sz, C.c_void_p, C.c_void_p]),
         ]:
             fn = getattr(L, name)
             fn.restype, fn.argtypes = res, args
@@ -267,6 +272,71 @@ def ef_mul(f, a, b):
     a, b = _u32(a), _u32(b); o = np.empty(4, dtype=np.uint32)
     lib().p3o_ef_mul(f, _ptr(a), _ptr(b), _ptr(o))
     return o
+
+
+def ef_inv(f, a):
+    a = _u32(a); o = np.empty(4, dtype=np.uint32)
+    lib().p3o_ef_inv(f, _ptr(a), _ptr(o))
+    return o
+
+
+def ef_add(f, a, b): return np.array([add(f, int(x), int(y)) for x, y in zip(a, b)], dtype=np.uint32)
+def ef_sub(f, a, b): return np.array([sub(f, int(x), int(y)) for x, y in zip(a, b)], dtype=np.uint32)
+def ef_from_base(f, x): return np.array([x, 0, 0, 0], dtype=np.uint32)
+
+
+def ef_pow(f, a, e):
+    r = ef_from_base(f, to_monty(f, 1)); a = _u32(a)
+    while e:
+        if e & 1: r = ef_mul(f, r, a)
+        a = ef_mul(f, a, a); e >>= 1
+    return r
+
+
+def open_inv_denoms(f, log_h, z):
+    z = _u32(z); out = np.empty((1 << log_h, 4), dtype=np.uint32)
+    lib().p3o_open_inv_denoms(f, log_h, _ptr(z), _ptr(out))
+    return out
+
+
+def columnwise_dot(f, mat, v):
+    mat, v = _u32(mat), _u32(v); out = np.empty((mat.shape[1], 4), dtype=np.uint32)
+    lib().p3o_columnwise_dot(f, _ptr(mat), mat.shape[0], mat.shape[1], _ptr(v), _ptr(out))
+    return out
+
+
+def rowwise_dot(f, mat, alpha):
+    mat, alpha = _u32(mat), _u32(alpha); out = np.empty((mat.shape[0], 4), dtype=np.uint32)
+    lib().p3o_rowwise_dot(f, _ptr(mat), mat.shape[0], mat.shape[1], _ptr(alpha), _ptr(out))
+    return out
+
+
+def open_reduce(f, ro, r, inv_denoms, coeff, yred):
+    ro = _u32(ro).copy(); r, inv_denoms, coeff, yred = _u32(r), _u32(inv_denoms), _u32(coeff), _u32(yred)
+    lib().p3o_open_reduce(f, _ptr(ro), _ptr(r), _ptr(inv_denoms), ro.shape[0], _ptr(coeff), _ptr(yred))
+    return ro
+
+
+def interpolate_coset(f, low_coset_bitrev, z, inv_denoms):
+    """interpolate_coset_with_precomputation (matrix/src/interpolation.rs:161-193) on the first h rows of a committed
+    (bit-reversed) LDE: f(z) = z (z^N - g^N) / (N g^N) * sum_i adjusted_i f(x_i), adjusted_i = 1/(z - x_i) - 1/z."""
+    m = _u32(low_coset_bitrev)
+    h = m.shape[0]; log_h = int(np.log2(h))
+    zinv = ef_inv(f, z)
+    adj = np.array([ef_sub(f, inv_denoms[i], zinv) for i in range(h)], dtype=np.uint32) if h <= 4096 else None
+    if adj is None:
+        adj = _u32(inv_denoms[:h]).copy()
+        for k in range(4):
+            col = adj[:, k].astype(np.int64) - int(zinv[k])
+            adj[:, k] = np.where(col < 0, col + prime(f), col).astype(np.uint32)
+    sums = columnwise_dot(f, m, adj)
+    g = generator(f)
+    z_pow_n = ef_pow(f, z, h)
+    g_pow_n = fpow(f, g, h)
+    denom_inv = inv(f, mul(f, g_pow_n, to_monty(f, h)))
+    scal = ef_mul(f, z, ef_sub(f, z_pow_n, ef_from_base(f, g_pow_n)))
+    scal = np.array([mul(f, int(c), denom_inv) for c in scal], dtype=np.uint32)
+    return np.array([ef_mul(f, scal, s_) for s_ in sums], dtype=np.uint32)
 
 
 def fold_matrix(f, vec_ef, log_arity, beta):

@@ -20,6 +20,7 @@ EXPORTS = [
     "p3gpu_poseidon2_set_constants", "p3gpu_poseidon2_permute_dev", "p3gpu_keccak_f_dev",
     "p3gpu_merkle_total_digests", "p3gpu_merkle_commit_dev", "p3gpu_merkle_commit", "p3gpu_merkle_from_digests_dev",
     "p3gpu_fri_fold_dev", "p3gpu_fri_fold", "p3gpu_ef_axpy_dev", "p3gpu_fri_commit_phase_dev", "p3gpu_pcs_commit_dev",
+    "p3gpu_open_inv_denoms_dev", "p3gpu_columnwise_dot_dev", "p3gpu_rowwise_dot_dev", "p3gpu_open_reduce_dev",
 ]
 
 
@@ -68,6 +69,10 @@ def load():
         "p3gpu_fri_fold": (i32, [vp, ci, vp, sz, cu, vp, vp]),
         "p3gpu_ef_axpy_dev": (i32, [vp, ci, vp, vp, sz, vp]),
         "p3gpu_fri_commit_phase_dev": (i32, [vp, ci, ci, vp, sz, cu, cu, cu, cu, vp, sz, vp, vp, vp, vp, vp]),
+        "p3gpu_open_inv_denoms_dev": (i32, [vp, ci, cu, vp, vp, vp, vp]),
+        "p3gpu_columnwise_dot_dev": (i32, [vp, ci, vp, sz, sz, vp, vp, vp]),
+        "p3gpu_rowwise_dot_dev": (i32, [vp, ci, vp, sz, sz, vp, vp]),
+        "p3gpu_open_reduce_dev": (i32, [vp, ci, vp, vp, vp, sz, vp, vp]),
         "p3gpu_pcs_commit_dev": (i32, [vp, ci, ci, vp, sz, sz, cu, vp, vp, vp, vp]),
     }
     for name, (res, args) in sig.items():

@@ -7,10 +7,10 @@ NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -ccbin /usr/bin/g++ $*"
 mkdir -p ../../build/obj
 pids=()
-for f in ntt hash fri capi; do
+for f in ntt hash fri open capi; do
   $NVCC $FLAGS -c $f.cu -o ../../build/obj/$f.o &
   pids+=($!)
 done
 for p in "${pids[@]}"; do wait $p; done
-$NVCC -gencode arch=compute_100a,code=sm_100a -shared -ccbin /usr/bin/g++ -o $OUT ../../build/obj/{ntt,hash,fri,capi}.o
+$NVCC -gencode arch=compute_100a,code=sm_100a -shared -ccbin /usr/bin/g++ -o $OUT ../../build/obj/{ntt,hash,fri,open,capi}.o
 echo "built $(realpath $OUT)"

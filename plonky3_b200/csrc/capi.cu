@@ -322,6 +322,27 @@ int32_t p3gpu_fri_commit_phase_dev(p3gpu_ctx *ctx, int field, int hash, uint32_t
     return P3GPU_OK;
 }
 
+// ---- Pcs::open (pre-FRI part) ------------------------------------------------------------------
+int32_t p3gpu_open_inv_denoms_dev(p3gpu_ctx *ctx, int field, unsigned log_height, const uint32_t z[4], const uint32_t *zinv,
+                                  uint32_t *d_inv_denoms, uint32_t *d_adjusted) {
+    P3_CHECK(ctx && z && d_inv_denoms, P3GPU_EINVAL, "null argument");
+    return open_inv_denoms(ctx, field, log_height, z, zinv, d_inv_denoms, d_adjusted);
+}
+int32_t p3gpu_columnwise_dot_dev(p3gpu_ctx *ctx, int field, const uint32_t *d_mat, size_t h, size_t w, const uint32_t *d_vec_ef,
+                                 const uint32_t *scale, uint32_t *d_out) {
+    P3_CHECK(ctx && d_mat && d_vec_ef && d_out, P3GPU_EINVAL, "null argument");
+    return open_columnwise_dot(ctx, field, d_mat, h, w, d_vec_ef, d_out, scale);
+}
+int32_t p3gpu_rowwise_dot_dev(p3gpu_ctx *ctx, int field, const uint32_t *d_mat, size_t h, size_t w, const uint32_t alpha[4], uint32_t *d_out) {
+    P3_CHECK(ctx && d_mat && alpha && d_out, P3GPU_EINVAL, "null argument");
+    return open_rowwise_dot(ctx, field, d_mat, h, w, alpha, d_out);
+}
+int32_t p3gpu_open_reduce_dev(p3gpu_ctx *ctx, int field, uint32_t *d_ro, const uint32_t *d_r, const uint32_t *d_inv_denoms, size_t h,
+                              const uint32_t coeff[4], const uint32_t yred[4]) {
+    P3_CHECK(ctx && d_ro && d_r && d_inv_denoms && coeff && yred, P3GPU_EINVAL, "null argument");
+    return open_reduce(ctx, field, d_ro, d_r, d_inv_denoms, h, coeff, yred);
+}
+
 // ---- Pcs::commit -------------------------------------------------------------------------------
 int32_t p3gpu_pcs_commit_dev(p3gpu_ctx *ctx, int field, int hash, const uint32_t *d_evals, size_t h, size_t w, unsigned log_blowup,
                              uint32_t *d_lde, uint32_t *d_layers, size_t *layer_lens, size_t *n_layers) {

@@ -1,0 +1,50 @@
+"""Host-side scalar arithmetic in EF4 = F[X]/(X^4 - W) (field/src/extension/binomial_extension.rs) for the handful of
+transcript-level values `open` needs (1/z, z^N, alpha powers, Mred(z)).  Elements are length-4 sequences of Montgomery u32
+words, exactly the wire/ABI representation; the arithmetic is done on canonical Python integers.  Not a compute path."""
+from __future__ import annotations
+
+import numpy as np
+
+from .field import Field
+
+
+def _c(field: Field, a): return [field.from_monty(int(v)) for v in a]
+def _m(field: Field, a): return np.array([field.to_monty(int(v)) for v in a], dtype=np.uint32)
+
+
+def ef_mul(field: Field, a, b):
+    p, x, y = field.P, _c(field, a), _c(field, b)
+    r = [0] * 7
+    for i in range(4):
+        for j in range(4):
+            r[i + j] = (r[i + j] + x[i] * y[j]) % p
+    return _m(field, [(r[i] + field.EXT_W * r[i + 4]) % p for i in range(3)] + [r[3]])
+
+
+def ef_add(field: Field, a, b): return _m(field, [(x + y) % field.P for x, y in zip(_c(field, a), _c(field, b))])
+def ef_sub(field: Field, a, b): return _m(field, [(x - y) % field.P for x, y in zip(_c(field, a), _c(field, b))])
+def ef_scale(field: Field, a, s_monty: int): return _m(field, [x * field.from_monty(s_monty) % field.P for x in _c(field, a)])
+def ef_from_base(field: Field, x_monty: int): return np.array([x_monty, 0, 0, 0], dtype=np.uint32)
+def ef_one(field: Field): return ef_from_base(field, field.ONE)
+
+
+def ef_pow(field: Field, a, e: int):
+    r, a = ef_one(field), np.asarray(a, dtype=np.uint32)
+    while e:
+        if e & 1:
+            r = ef_mul(field, r, a)
+        a = ef_mul(field, a, a); e >>= 1
+    return r
+
+
+def ef_inv(field: Field, a):
+    """a^-1 = a^(p^4 - 2)."""
+    return ef_pow(field, a, field.P ** 4 - 2)
+
+
+def ef_dot_powers(field: Field, alpha, ys):
+    """sum_i alpha^i * ys[i] (dot_product(alpha.powers(), openings), two_adic_pcs.rs:636-637)."""
+    acc, pw = np.zeros(4, dtype=np.uint32), ef_one(field)
+    for y in ys:
+        acc = ef_add(field, acc, ef_mul(field, pw, y)); pw = ef_mul(field, pw, alpha)
+    return acc

@@ -186,6 +186,70 @@ class TwoAdicFriPcs:
                 raise ValueError(f"committed LDE height {lde.shape[0]} is smaller than the blowup factor {min_height}")
         return self.mmcs.commit(ldes)
 
+    def open_values_and_fri_inputs(self, data_with_points: list, challenger):
+        """The pre-FRI part of TwoAdicFriPcs::open (two_adic_pcs.rs:413-662) with the LDEs resident on the device.
+
+        data_with_points: list of (prover_data, points_per_matrix) — prover_data a MerkleTree whose leaves are CUDA matrices
+        (committed bit-reversed LDEs), points_per_matrix[i] the EF4 points (4 Montgomery words each) matrix i is opened at.
+        challenger protocol: observe_algebra_slice(ys), sample_algebra_element().
+        Returns (all_opened_values[round][matrix][point] -> (width, 4) array, fri_inputs: list of (len, 4) CUDA vectors in
+        descending length — the `fri_input` handed to prove_fri / commit_phase)."""
+        from . import extension as X
+        import torch
+        f, gpu = self.dft.field, self.dft.gpu
+        rounds = [(self.mmcs.get_matrices(data), points) for data, points in data_with_points]
+        for mats, points in rounds:
+            assert len(mats) == len(points), "each matrix should have a corresponding set of evaluation points"
+        log_global_max_height = _log2_strict(max(int(m.shape[0]) for mats, _ in rounds for m in mats))
+        # compute_inverse_denominators (:743-780): one vector per unique point, for the tallest matrix opened there
+        max_lh = {}
+        for mats, points in rounds:
+            for m, pts in zip(mats, points):
+                for z in pts:
+                    k = tuple(int(v) for v in z)
+                    max_lh[k] = max(max_lh.get(k, 0), _log2_strict(int(m.shape[0])))
+        inv_denoms, adjusted = {}, {}
+        for k, lh in max_lh.items():
+            z = np.array(k, dtype=np.uint32)
+            inv_denoms[k], adjusted[k] = gpu.open_inv_denoms(f.id, lh, z, X.ef_inv(f, z))
+        # opened values by barycentric interpolation of the low coset (:496-563; interpolation.rs:161-193)
+        all_opened = []
+        for mats, points in rounds:
+            per_mat = []
+            for m, pts in zip(mats, points):
+                h = int(m.shape[0]) >> self.fri.log_blowup
+                log_h = _log2_strict(h)
+                per_pt = []
+                for z in pts:
+                    k = tuple(int(v) for v in z)
+                    z = np.array(k, dtype=np.uint32)
+                    g_pow_n = f.pow(f.generator, h)
+                    denom_inv = f.inv(f.mul(g_pow_n, f.to_monty(h)))
+                    scal = X.ef_scale(f, X.ef_mul(f, z, X.ef_sub(f, X.ef_pow(f, z, 1 << log_h), X.ef_from_base(f, g_pow_n))), denom_inv)
+                    ys = gpu.columnwise_dot(f.id, m[:h], adjusted[k], scal).cpu().numpy().view(np.uint32)
+                    challenger.observe_algebra_slice(ys)
+                    per_pt.append(ys)
+                per_mat.append(per_pt)
+            all_opened.append(per_mat)
+        alpha = np.asarray(challenger.sample_algebra_element(), dtype=np.uint32)
+        # reduced openings per height (:598-660)
+        num_reduced, reduced = {}, {}
+        for (mats, points), opened_round in zip(rounds, all_opened):
+            for m, pts, opened_mat in zip(mats, points, opened_round):
+                H = int(m.shape[0]); lh = _log2_strict(H)
+                if lh not in reduced:
+                    reduced[lh] = torch.zeros((H, 4), dtype=torch.int32, device=m.device)
+                    num_reduced[lh] = 0
+                r = gpu.rowwise_dot(f.id, m, alpha)                              # Mred(x) for every row
+                for z, ys in zip(pts, opened_mat):
+                    k = tuple(int(v) for v in z)
+                    coeff = X.ef_pow(f, alpha, num_reduced[lh])                  # alpha_pow_offset
+                    yred = X.ef_dot_powers(f, alpha, ys)                         # Mred(z)
+                    gpu.open_reduce(f.id, reduced[lh], r, inv_denoms[k], coeff, yred)
+                    num_reduced[lh] += int(m.shape[1])
+        fri_inputs = [reduced[lh] for lh in sorted(reduced, reverse=True)]
+        return all_opened, fri_inputs
+
     def get_evaluations_on_domain(self, prover_data, idx: int, domain):
         """two_adic_pcs.rs:376-385 fast path: first |domain| rows of the committed bit-reversed LDE."""
         shift, log_size = domain

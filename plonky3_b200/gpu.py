@@ -202,6 +202,48 @@ class Gpu:
             out.append(caps[off:off + cap_lens[k]].copy()); off += cap_lens[k]
         return out, [int(las[k]) for k in range(nr.value)], final
 
+    # ------------------------------------------------------------------ Pcs::open (pre-FRI part)
+    @staticmethod
+    def _ef(a):
+        a = np.ascontiguousarray(a, dtype=np.uint32)
+        assert a.size == 4
+        return a
+
+    def open_inv_denoms(self, field, log_height, z, zinv=None):
+        """(inv_denoms, adjusted or None): CUDA (2^log_height, 4) tensors, bit-reversed coset order."""
+        self._use_torch_stream()
+        zz = self._ef(z)
+        inv = self._empty((1 << log_height, 4))
+        adj = self._empty((1 << log_height, 4)) if zinv is not None else None
+        zi = self._ef(zinv) if zinv is not None else None
+        check(self.L.p3gpu_open_inv_denoms_dev(self.h, field, log_height, zz.ctypes.data, zi.ctypes.data if zi is not None else None,
+                                               inv.data_ptr(), adj.data_ptr() if adj is not None else None))
+        return inv, adj
+
+    def columnwise_dot(self, field, mat, vec_ef, scale=None):
+        m, v = self._dev(mat), self._dev(vec_ef); self._use_torch_stream()
+        assert v.shape[0] >= m.shape[0]
+        out = self._empty((int(m.shape[1]), 4))
+        sc = self._ef(scale) if scale is not None else None
+        check(self.L.p3gpu_columnwise_dot_dev(self.h, field, m.data_ptr(), m.shape[0], m.shape[1], v.data_ptr(),
+                                              sc.ctypes.data if sc is not None else None, out.data_ptr()))
+        return out
+
+    def rowwise_dot(self, field, mat, alpha):
+        m = self._dev(mat); self._use_torch_stream()
+        out = self._empty((int(m.shape[0]), 4))
+        a = self._ef(alpha)
+        check(self.L.p3gpu_rowwise_dot_dev(self.h, field, m.data_ptr(), m.shape[0], m.shape[1], a.ctypes.data, out.data_ptr()))
+        return out
+
+    def open_reduce(self, field, ro, r, inv_denoms, coeff, yred):
+        a, b, c = self._dev(ro), self._dev(r), self._dev(inv_denoms); self._use_torch_stream()
+        h = int(a.shape[0])
+        assert b.shape[0] == h and c.shape[0] >= h
+        check(self.L.p3gpu_open_reduce_dev(self.h, field, a.data_ptr(), b.data_ptr(), c.data_ptr(), h,
+                                           self._ef(coeff).ctypes.data, self._ef(yred).ctypes.data))
+        return a
+
     def pcs_commit(self, field, hash_kind, evals_dev, log_blowup):
         """TwoAdicFriPcs::commit for one matrix over the subgroup H, fully device resident.
         Returns (lde tensor (h<<log_blowup, w) bit-reversed rows, digest layers)."""

@@ -209,24 +209,37 @@ def replay(backend):
     for v in quot_root: ch.observe(v)
     zeta = ch.sample_ef(); zeta_n = escal(zeta, w8)
 
-    # --- openings (host side): evaluate at zeta / zeta*w
-    qcoef = [[c * pow(inv(GEN), i, P) % P for i, c in enumerate(idft8([Q[i][k] for i in range(8)]))] for k in range(4)]
-    y1 = [evalp_e(c, zeta) for c in tcoef]; y2 = [evalp_e(c, zeta_n) for c in tcoef]; y3 = [evalp_e(c, zeta) for c in qcoef]
-    for ys in (y1, y2, y3):
-        for y in ys:
-            for v in y: ch.observe(v)
-    al = ch.sample_ef(); alp = [[1, 0, 0, 0]]
-    for _ in range(8): alp.append(emul(alp[-1], al))
-    xb = [GEN * pow(w32, br(i, 5), P) % P for i in range(32)]
-    ro = [[0] * 4 for _ in range(32)]; nred = 0
-    for mat, wd, z, ys in ((lde, 2, zeta, y1), (lde, 2, zeta_n, y2), (qlde, 4, zeta, y3)):   # two_adic_pcs.rs:606-661
-        yred = [0] * 4
-        for i in range(wd): yred = eadd(yred, emul(alp[i], ys[i]))
-        for r in range(32):
-            rr = [0] * 4
-            for i in range(wd): rr = eadd(rr, escal(alp[i], mat[r][i]))
-            ro[r] = eadd(ro[r], emul(alp[nred], emul(esub(yred, rr), einv(esub(z, eF(xb[r]))))))
-        nred += wd
+    # --- openings.  With backend.open (TwoAdicFriPcs::open's pre-FRI part on the hot-path backend: inverse denominators,
+    #     barycentric interpolation of the low coset, alpha-compression + quotient accumulation) the values below come from
+    #     the backend; otherwise they are evaluated here from the polynomial coefficients (pure Python).
+    if hasattr(backend, "open"):
+        class _Adapter:                                                # challenger protocol of plonky3_b200.fri
+            def observe_algebra_slice(self, ys):
+                for y in np.asarray(ys).reshape(-1, 4):
+                    for v in y: ch.observe(from_m(int(v)))
+            def sample_algebra_element(self): return [to_m(v) for v in ch.sample_ef()]
+        zm = np.array([to_m(v) for v in zeta], dtype=np.uint32); znm = np.array([to_m(v) for v in zeta_n], dtype=np.uint32)
+        opened, fri_inputs = backend.open([([trace_lde_m], [[zm, znm]]), ([quot_lde_m], [[zm]])], _Adapter(), 2)
+        y1, y2, y3 = _c_rows(opened[0][0][0]), _c_rows(opened[0][0][1]), _c_rows(opened[1][0][0])
+        ro = _c_rows(fri_inputs[0])
+    else:
+        qcoef = [[c * pow(inv(GEN), i, P) % P for i, c in enumerate(idft8([Q[i][k] for i in range(8)]))] for k in range(4)]
+        y1 = [evalp_e(c, zeta) for c in tcoef]; y2 = [evalp_e(c, zeta_n) for c in tcoef]; y3 = [evalp_e(c, zeta) for c in qcoef]
+        for ys in (y1, y2, y3):
+            for y in ys:
+                for v in y: ch.observe(v)
+        al = ch.sample_ef(); alp = [[1, 0, 0, 0]]
+        for _ in range(8): alp.append(emul(alp[-1], al))
+        xb = [GEN * pow(w32, br(i, 5), P) % P for i in range(32)]
+        ro = [[0] * 4 for _ in range(32)]; nred = 0
+        for mat, wd, z, ys in ((lde, 2, zeta, y1), (lde, 2, zeta_n, y2), (qlde, 4, zeta, y3)):   # two_adic_pcs.rs:606-661
+            yred = [0] * 4
+            for i in range(wd): yred = eadd(yred, emul(alp[i], ys[i]))
+            for r in range(32):
+                rr = [0] * 4
+                for i in range(wd): rr = eadd(rr, escal(alp[i], mat[r][i]))
+                ro[r] = eadd(ro[r], emul(alp[nred], emul(esub(yred, rr), einv(esub(z, eF(xb[r]))))))
+            nred += wd
 
     # --- FRI commit phase round 0: commit (16 x 2 EF = 16 x 8 base), grind, beta, fold   (fri/src/prover.rs:219-266)
     ro_m = _m_arr(ro)                                                 # (32, 4)
