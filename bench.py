@@ -315,7 +315,27 @@ def main():
         xt = torch.randint(0, KB.P, (1 << 20, 1312), device=dev, dtype=torch.int32, generator=g)
         t_trace, nl = timed(lambda: gpu.pcs_commit(KB.id, _lib.HASH_POSEIDON2_W24, xt, 1), 2, 1)
         tl, _ = timed(lambda: gpu.coset_lde_batch(KB.id, xt, 1, KB.generator), 2, 1)
+        # pcs.open pre-FRI work on the resident LDE: two opening points (zeta, zeta*g) like uni-stark
+        lde_t = gpu.coset_lde_batch(KB.id, xt, 1, KB.generator)
         del xt
+        from plonky3_b200 import extension as X
+        zs = [np.array([11, 22, 33, 44], dtype=np.uint32), np.array([55, 66, 77, 88], dtype=np.uint32)]
+        al = np.array([5, 6, 7, 8], dtype=np.uint32)
+        t_inv, _ = timed(lambda: gpu.open_inv_denoms(KB.id, 21, zs[0], X.ef_inv(KB, zs[0])), k, 1)
+        invd, adj = gpu.open_inv_denoms(KB.id, 21, zs[0], X.ef_inv(KB, zs[0]))
+        low = lde_t[: 1 << 20]
+        t_col, _ = timed(lambda: gpu.columnwise_dot(KB.id, low, adj), k, 1)
+        t_row, _ = timed(lambda: gpu.rowwise_dot(KB.id, lde_t, al), k, 1)
+        rr = gpu.rowwise_dot(KB.id, lde_t, al); ro = torch.zeros((1 << 21, 4), dtype=torch.int32, device=dev)
+        t_red, _ = timed(lambda: gpu.open_reduce(KB.id, ro, rr, invd, al, al), k, 1)
+        col_bytes, row_bytes = (1 << 20) * 1312 * 4 + (1 << 20) * 16, (1 << 21) * 1312 * 4 + (1 << 21) * 16
+        open_ms = 2 * (t_inv + t_col + t_red) + t_row
+        others["config5_open_pre_fri_kb_2^21x1312"] = {
+            "inv_denoms_ms": t_inv, "columnwise_dot_ms": t_col, "columnwise_dot_GBps": col_bytes / t_col / 1e6,
+            "rowwise_dot_ms": t_row, "rowwise_dot_GBps": row_bytes / t_row / 1e6, "reduce_ms": t_red,
+            "open_two_points_ms": open_ms, "hbm_peak_GBps": peak,
+            "note": "barycentric evaluation at 2 points + alpha compression + quotient accumulation over the resident trace LDE; HBM-bound streaming reductions"}
+        del lde_t, invd, adj, rr, ro, low
         xq = torch.randint(0, KB.P, (1 << 20, 4), device=dev, dtype=torch.int32, generator=g)
         def quot():
             a_ = gpu.coset_lde_batch(KB.id, xq, 1, KB.generator); b_ = gpu.coset_lde_batch(KB.id, xq, 1, KB.generator)
