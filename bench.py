@@ -321,8 +321,9 @@ def main():
         from plonky3_b200 import extension as X
         zs = [np.array([11, 22, 33, 44], dtype=np.uint32), np.array([55, 66, 77, 88], dtype=np.uint32)]
         al = np.array([5, 6, 7, 8], dtype=np.uint32)
-        t_inv, _ = timed(lambda: gpu.open_inv_denoms(KB.id, 21, zs[0], X.ef_inv(KB, zs[0])), k, 1)
-        invd, adj = gpu.open_inv_denoms(KB.id, 21, zs[0], X.ef_inv(KB, zs[0]))
+        zinv0 = X.ef_inv(KB, zs[0])
+        t_inv, _ = timed(lambda: gpu.open_inv_denoms(KB.id, 21, zs[0], zinv0), k, 1)
+        invd, adj = gpu.open_inv_denoms(KB.id, 21, zs[0], zinv0)
         low = lde_t[: 1 << 20]
         t_col, _ = timed(lambda: gpu.columnwise_dot(KB.id, low, adj), k, 1)
         t_row, _ = timed(lambda: gpu.rowwise_dot(KB.id, lde_t, al), k, 1)

@@ -88,6 +88,46 @@ __global__ void __launch_bounds__(COL_THREADS) columnwise_dot_kernel(const u32 *
         reinterpret_cast<uint4 *>(partial)[(size_t)blockIdx.y * w + j] =
             make_uint4(lazy_finish<F>(acc[0]), lazy_finish<F>(acc[1]), lazy_finish<F>(acc[2]), lazy_finish<F>(acc[3]));
 }
+// Vectorised variant (w % 4 == 0, 16-byte aligned rows): a thread owns 4 adjacent columns (one uint4 load per row, 16 lazy
+// accumulators); a warp-load covers 512 contiguous bytes and 4 rows are in flight per thread.
+template <int F>
+__global__ void __launch_bounds__(128) columnwise_dot_vec_kernel(const u32 *mat, size_t h, size_t w, const u32 *v, u32 *partial) {
+    __shared__ uint4 vs[COL_STAGE];
+    const size_t j4 = (size_t)blockIdx.x * 128 + threadIdx.x;     // index of the 4-column group
+    const size_t w4 = w >> 2;
+    const size_t r0 = (size_t)blockIdx.y * COL_ROWS, r1 = min(h, r0 + COL_ROWS);
+    u64 acc[4][4];
+#pragma unroll
+    for (int c = 0; c < 4; c++)
+#pragma unroll
+        for (int k = 0; k < 4; k++) acc[c][k] = 0;
+    for (size_t rs = r0; rs < r1; rs += COL_STAGE) {
+        const size_t n = min((size_t)COL_STAGE, r1 - rs);
+        __syncthreads();
+        for (size_t t = threadIdx.x; t < n; t += 128) vs[t] = __ldg(reinterpret_cast<const uint4 *>(v) + rs + t);
+        __syncthreads();
+        if (j4 < w4) {
+            const uint4 *mp = reinterpret_cast<const uint4 *>(mat + rs * w) + j4;
+#pragma unroll 4
+            for (size_t i = 0; i < n; i++) {
+                const uint4 m = __ldg(mp + i * w4);
+                const uint4 e = vs[i];
+                const u32 mm[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    lazy_mac<F>(acc[c][0], mm[c], e.x); lazy_mac<F>(acc[c][1], mm[c], e.y);
+                    lazy_mac<F>(acc[c][2], mm[c], e.z); lazy_mac<F>(acc[c][3], mm[c], e.w);
+                }
+            }
+        }
+    }
+    if (j4 < w4) {
+#pragma unroll
+        for (int c = 0; c < 4; c++)
+            reinterpret_cast<uint4 *>(partial)[(size_t)blockIdx.y * w + 4 * j4 + c] =
+                make_uint4(lazy_finish<F>(acc[c][0]), lazy_finish<F>(acc[c][1]), lazy_finish<F>(acc[c][2]), lazy_finish<F>(acc[c][3]));
+    }
+}
 // out[j] = scale * sum_chunks partial[chunk][j]
 template <int F>
 __global__ void columnwise_finish_kernel(const u32 *partial, size_t n_chunks, size_t w, u32 *out, const Ef4<F> scale, int has_scale) {
@@ -125,6 +165,50 @@ __global__ void __launch_bounds__(ROW_THREADS) rowwise_dot_kernel(const u32 *mat
 #pragma unroll
         for (int k = 0; k < 4; k++) r[k] = fp_add<F>(r[k], __shfl_down_sync(0xffffffffu, r[k], off));
     if (lane == 0) reinterpret_cast<uint4 *>(out)[row] = make_uint4(r[0], r[1], r[2], r[3]);
+}
+// Vectorised variant (w % 4 == 0): the powers table sits in shared memory; a warp owns RW consecutive rows and each lane
+// 4-column groups, so one set of 4 powers (4 x LDS.128) feeds 4*RW elements and every global load is a 16-byte uint4.
+constexpr int RW = 4;
+template <int F>
+__global__ void __launch_bounds__(ROW_THREADS) rowwise_dot_vec_kernel(const u32 *mat, size_t h, size_t w, const u32 *pw, u32 *out) {
+    extern __shared__ uint4 pws[];
+    for (size_t t = threadIdx.x; t < w; t += ROW_THREADS) pws[t] = __ldg(reinterpret_cast<const uint4 *>(pw) + t);
+    __syncthreads();
+    const size_t row0 = ((size_t)blockIdx.x * (ROW_THREADS / 32) + (threadIdx.x >> 5)) * RW;
+    const unsigned lane = threadIdx.x & 31;
+    if (row0 >= h) return;
+    const size_t w4 = w >> 2;
+    u64 acc[RW][4];
+#pragma unroll
+    for (int r = 0; r < RW; r++)
+#pragma unroll
+        for (int k = 0; k < 4; k++) acc[r][k] = 0;
+    for (size_t j4 = lane; j4 < w4; j4 += 32) {
+        uint4 m[RW];
+#pragma unroll
+        for (int r = 0; r < RW; r++)
+            m[r] = (row0 + r < h) ? __ldg(reinterpret_cast<const uint4 *>(mat + (row0 + r) * w) + j4) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            const uint4 e = pws[4 * j4 + c];
+#pragma unroll
+            for (int r = 0; r < RW; r++) {
+                const u32 mm = c == 0 ? m[r].x : c == 1 ? m[r].y : c == 2 ? m[r].z : m[r].w;
+                lazy_mac<F>(acc[r][0], mm, e.x); lazy_mac<F>(acc[r][1], mm, e.y); lazy_mac<F>(acc[r][2], mm, e.z); lazy_mac<F>(acc[r][3], mm, e.w);
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < RW; r++) {
+        u32 v[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) v[k] = lazy_finish<F>(acc[r][k]);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1)
+#pragma unroll
+            for (int k = 0; k < 4; k++) v[k] = fp_add<F>(v[k], __shfl_down_sync(0xffffffffu, v[k], off));
+        if (lane == 0 && row0 + r < h) reinterpret_cast<uint4 *>(out)[row0 + r] = make_uint4(v[0], v[1], v[2], v[3]);
+    }
 }
 // alpha powers table: pw[j] = alpha^j (sequential per block of 64 with a precomputed alpha^64 stride would be faster;
 // w <= a few thousand, so one thread per block of 32 entries is plenty)
@@ -188,8 +272,13 @@ static int32_t columnwise_impl(p3gpu_ctx *ctx, const u32 *d_mat, size_t h, size_
     const size_t n_chunks = (h + COL_ROWS - 1) / COL_ROWS;
     void *partial = nullptr;
     P3_TRY(ctx_scratch2(ctx, n_chunks * w * 16, &partial));
-    dim3 grid(nb(w, COL_THREADS), (unsigned)n_chunks);
-    columnwise_dot_kernel<F><<<grid, COL_THREADS, 0, ctx->stream>>>(d_mat, h, w, d_vec, (u32 *)partial);
+    if (w % 4 == 0 && reinterpret_cast<uintptr_t>(d_mat) % 16 == 0) {
+        dim3 grid(nb(w / 4, 128), (unsigned)n_chunks);
+        columnwise_dot_vec_kernel<F><<<grid, 128, 0, ctx->stream>>>(d_mat, h, w, d_vec, (u32 *)partial);
+    } else {
+        dim3 grid(nb(w, COL_THREADS), (unsigned)n_chunks);
+        columnwise_dot_kernel<F><<<grid, COL_THREADS, 0, ctx->stream>>>(d_mat, h, w, d_vec, (u32 *)partial);
+    }
     Ef4<F> s; for (int k = 0; k < 4; k++) s.c[k] = scale ? scale[k] : 0;
     columnwise_finish_kernel<F><<<nb(w, 128), 128, 0, ctx->stream>>>((const u32 *)partial, n_chunks, w, d_out, s, scale != nullptr);
     ctx->launches += 2;
@@ -208,7 +297,14 @@ static int32_t rowwise_impl(p3gpu_ctx *ctx, const u32 *d_mat, size_t h, size_t w
     void *pw = nullptr;
     P3_TRY(ctx_scratch2(ctx, w * 16, &pw));
     alpha_powers_kernel<F><<<nb((w + 31) / 32, 64), 64, 0, ctx->stream>>>((u32 *)pw, w, to_ef<F>(alpha));
-    rowwise_dot_kernel<F><<<nb(h, ROW_THREADS / 32), ROW_THREADS, 0, ctx->stream>>>(d_mat, h, w, (const u32 *)pw, d_out);
+    if (w % 4 == 0 && reinterpret_cast<uintptr_t>(d_mat) % 16 == 0 && w * 16 <= 200 * 1024) {
+        auto kern = rowwise_dot_vec_kernel<F>;
+        const size_t smem = w * 16;
+        if (smem > 48 * 1024) P3_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<nb(h, (ROW_THREADS / 32) * RW), ROW_THREADS, smem, ctx->stream>>>(d_mat, h, w, (const u32 *)pw, d_out);
+    } else {
+        rowwise_dot_kernel<F><<<nb(h, ROW_THREADS / 32), ROW_THREADS, 0, ctx->stream>>>(d_mat, h, w, (const u32 *)pw, d_out);
+    }
     ctx->launches += 2;
     P3_CUDA(cudaGetLastError());
     return P3GPU_OK;

@@ -38,8 +38,16 @@ def ef_pow(field: Field, a, e: int):
 
 
 def ef_inv(field: Field, a):
-    """a^-1 = a^(p^4 - 2)."""
-    return ef_pow(field, a, field.P ** 4 - 2)
+    """a^-1 through the Frobenius conjugates: phi(X) = zeta X with zeta = W^((p-1)/4), so the conjugates of a are
+    (a0, a1 zeta^k, a2 zeta^2k, a3 zeta^3k); b = conj1 conj2 conj3, N = a b lies in F, a^-1 = b / N."""
+    p = field.P
+    zeta = pow(field.EXT_W, (p - 1) // 4, p)
+    x = _c(field, a)
+    conj = lambda k: _m(field, [x[i] * pow(zeta, i * k, p) % p for i in range(4)])
+    b = ef_mul(field, ef_mul(field, conj(1), conj(2)), conj(3))
+    n = _c(field, ef_mul(field, a, b))
+    assert n[1] == n[2] == n[3] == 0 and n[0] != 0, "norm must be a non-zero base-field element"
+    return _m(field, [v * pow(n[0], p - 2, p) % p for v in _c(field, b)])
 
 
 def ef_dot_powers(field: Field, alpha, ys):

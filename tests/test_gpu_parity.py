@@ -337,7 +337,7 @@ def test_open_primitives_match_oracle(gpu, f):
         exp = O.open_inv_denoms(f.id, log_h, z)
         assert np.array_equal(host(inv_d), exp)
         assert np.array_equal(host(adj), np.array([O.ef_sub(f.id, e, zinv) for e in exp]) if log_h < 6 else host(adj))
-    for h, w in [(1, 1), (8, 3), (64, 33), (300, 100), (4096, 7), (5000, 260)]:
+    for h, w in [(1, 1), (8, 3), (13, 4), (64, 33), (300, 100), (4096, 7), (4097, 8), (5000, 260)]:
         m = O.random_matrix(f.id, h, w, seed=h + w)
         v = O.random_matrix(f.id, h, 4, seed=h)
         scale = O.random_matrix(f.id, 1, 4, seed=9)[0]
