@@ -21,10 +21,14 @@ namespace p3 {
 // =================================================================================================
 // Poseidon2
 // =================================================================================================
+// Montgomery product left in (0, 2p): hi(ab) - hi(t p) + p is one IADD3, no conditional correction.  Safe as ONE factor of
+// a following product (2p * p < p * 2^32), which then returns to the canonical range.
+template <int F> __device__ __forceinline__ u32 mont_mul_lazy(u32 a, u32 b) { return mont_redc_lazy<F>((u64)a * b) + Fp<F>::P; }
+
 template <int F> __device__ __forceinline__ u32 sbox(u32 x) {
-    const u32 x2 = mont_mul<F>(x, x);
-    const u32 x3 = mont_mul<F>(x2, x);
-    if (Fp<F>::SBOX_D == 3) return x3;
+    if (Fp<F>::SBOX_D == 3) return mont_mul<F>(mont_mul_lazy<F>(x, x), x);          // x^3: the square stays lazy
+    const u32 x2 = mont_mul<F>(x, x);                                                // x^7 = x^4 * x^3, x^3 lazy
+    const u32 x3 = mont_mul_lazy<F>(x2, x);
     const u32 x4 = mont_mul<F>(x2, x2);
     return mont_mul<F>(x4, x3);
 }
@@ -72,23 +76,31 @@ template <> struct Diag<KOALA_BEAR, 24> { static __host__ __device__ constexpr D
     constexpr DiagEntry d[24] = {{-2,0},{1,0},{2,0},{1,-1},{3,0},{4,0},{-1,-1},{-3,0},{-4,0},{1,-8},{1,-2},{1,-3},{1,-4},{1,-5},{1,-6},{1,-24},{-1,-8},{-1,-3},{-1,-4},{-1,-5},{-1,-6},{-1,-7},{-1,-9},{-1,-24}};
     return d[i]; } };
 
-// x * 2^-k for a Montgomery value x: redc(x << (32-k)) = x * 2^(32-k) * 2^-32  (monty-31 div_2exp_u64)
+// x * 2^-k (monty-31 div_2exp_u64).  Both primes are p = 2^31 - 2^L + 1 (L = 24 KoalaBear, 27 BabyBear), so p = 1 mod 2^k for
+// k <= L and the exact quotient is (x + m*p) >> k with m = (-x) mod 2^k:
+//     x / 2^k = ceil(x / 2^k) + m * (2^(31-k) - 2^(L-k))            (result < p for x < p)
+// = 2 logic/shift ops + 1 add + 1 IMAD, no IMAD.HI (a Montgomery reduction of x << (32-k) costs IMAD + IMAD.HI + 4 ALU ops).
+// It is representation-independent: dividing the Montgomery form by 2^k divides the value by 2^k.
 template <int F, int K> __device__ __forceinline__ u32 div_2exp(u32 x) {
-    return mont_redc<F>((u64)x << (32 - K));
+    constexpr int L = (F == KOALA_BEAR) ? 24 : 27;
+    static_assert(K >= 1 && K <= L, "shift exceeds the 2-adic part of p - 1");
+    constexpr u32 mask = (1u << K) - 1u;
+    constexpr u32 C = (1u << (31 - K)) - (1u << (L - K));
+    const u32 m = (0u - x) & mask;
+    const u32 c = (x + mask) >> K;
+    return c + m * C;
 }
 template <int F, int W, int I> __device__ __forceinline__ u32 diag_mul_add(u32 x, u32 sum) {
     constexpr DiagEntry d = Diag<F, W>::at(I);
     constexpr int am = d.mul < 0 ? -d.mul : d.mul;
     u32 v;
-    if (d.shift == 0) {
+    if constexpr (d.shift == 0) {
         v = x;
         if (am == 2) v = fp_double<F>(x);
         if (am == 3) v = fp_add<F>(fp_double<F>(x), x);
         if (am == 4) v = fp_double<F>(fp_double<F>(x));
-    } else if (d.shift == -1) {
-        v = fp_halve<F>(x);
     } else {
-        v = div_2exp<F, -d.shift>(x);
+        v = div_2exp<F, -d.shift>(x);   // also covers the halves (k = 1)
     }
     return d.mul < 0 ? fp_sub<F>(sum, v) : fp_add<F>(sum, v);
 }

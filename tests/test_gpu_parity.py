@@ -98,6 +98,17 @@ def test_coset_lde_matches_oracle(gpu, f, log_h, w, added_bits):
     assert np.array_equal(dft.lde_batch(m, added_bits).bit_reverse_rows(), O.coset_lde_batch(f.id, m, added_bits, f.ONE, True))
 
 
+@pytest.mark.parametrize("f,log_h,w", [(BabyBear, 22, 3), (KoalaBear, 21, 4), (BabyBear, 23, 1), (KoalaBear, 17, 24), (BabyBear, 19, 20)])
+def test_large_heights_three_pass_plans(gpu, f, log_h, w):
+    # heights above 2^20 run as three passes (7+7+7, 8+7+7, 8+8+7 layers); BASELINE config 4 is 2^22 rows
+    dft = Radix2DitParallel(f, gpu)
+    m = O.random_matrix(f.id, 1 << log_h, w, seed=log_h)
+    assert np.array_equal(dft.dft_batch(m), O.dft_batch(f.id, m))
+    if log_h <= 22:
+        got = dft.coset_lde_batch(dev(m), 1, f.generator).bit_reverse_rows()
+        assert np.array_equal(host(got), O.coset_lde_batch(f.id, m, 1, f.generator, bitrev_out=True))
+
+
 def test_dft_shape_errors(gpu):
     # the reference panics in log2_strict_usize on non power-of-two heights; the C ABI returns P3GPU_EINVAL
     with pytest.raises(P.P3GpuError, match="power of two"):
