@@ -38,6 +38,8 @@ struct PassArgs {
     u32 ct;        // tile width of the generic-width kernel variant
     u32 n_cosets;  // cosets batched in this launch (fastest-varying part of blockIdx.x)
     u32 vec16;     // fast kernel: row segments are 16-byte aligned (cp.async 16)
+    u32 skip_load, skip_store;  // profiling experiments only
+    u32 skip_bfly; // profiling experiment only (P3GPU_NTT_NOBFLY=1): move the data, skip the butterflies
     int log_n, l0, l1;
     const uint2 *tw;  // heap-ordered twiddles of coset 0
     int in_bitrev, out_bitrev;
@@ -223,7 +225,7 @@ template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 //   * all tiles of a pass have the same runtime width ct (16/20/24 columns; w = 100 -> 5 x 20) so that ONE launch covers
 //     every column and neighbouring tiles share DRAM bursts through L2.
 template <int F, int R_LOG, int CT_T, int THREADS, int NBUF>   // CT_T: compile-time tile width (16/20/24) or 0 = runtime a.ct
-__global__ void __launch_bounds__(THREADS, (NBUF == 1 && THREADS <= 384) ? 2 : 1) ntt_pass_fast_kernel(const __grid_constant__ PassArgs a) {
+__global__ void __launch_bounds__(THREADS, NBUF == 2 ? 1 : (CT_T == 16 && THREADS == 256) ? 3 : 2) ntt_pass_fast_kernel(const __grid_constant__ PassArgs a) {
     constexpr int Q2 = (R_LOG + 1) / 2, Q1 = R_LOG - Q2;
     constexpr u32 E1 = 1u << Q1, E2 = 1u << Q2, R = 1u << R_LOG;
     const u32 CT = CT_T ? (u32)CT_T : a.ct;
@@ -313,7 +315,7 @@ __global__ void __launch_bounds__(THREADS, (NBUF == 1 && THREADS <= 384) ? 2 : 1
             if (t + gridDim.x < total) { issue(t + gridDim.x, buf ^ 1u); cp_async_wait<1>(); }
             else cp_async_wait<0>();
         } else {   // single buffer: other resident CTAs of this SM compute while this one waits for its tile
-            issue(t, 0);
+            if (!a.skip_load) issue(t, 0);
             cp_async_wait<0>();
         }
         __syncthreads();
@@ -334,7 +336,7 @@ __global__ void __launch_bounds__(THREADS, (NBUF == 1 && THREADS <= 384) ? 2 : 1
 #pragma unroll
                     for (u32 m = 0; m < E1; m++) x[m] = shoup_mul<F>(x[m], a.scale);
                 }
-                reg_network<F, Q1>(x, tws, 1u);
+                if (!a.skip_bfly) reg_network<F, Q1>(x, tws, 1u);
 #pragma unroll
                 for (u32 m = 0; m < E1; m++) sp[m * gstride] = x[m];
                 c += dc; g += dg;
@@ -354,7 +356,7 @@ __global__ void __launch_bounds__(THREADS, (NBUF == 1 && THREADS <= 384) ? 2 : 1
                 u32 x[E2];
 #pragma unroll
                 for (u32 m = 0; m < E2; m++) x[m] = sp[m * CT];
-                reg_network<F, Q2>(x, tws, E1 + g);
+                if (!a.skip_bfly) reg_network<F, Q2>(x, tws, E1 + g);
                 if (a.final_reduce) {
 #pragma unroll
                     for (u32 m = 0; m < E2; m++) x[m] = fp_reduce<F>(x[m]);
@@ -363,7 +365,11 @@ __global__ void __launch_bounds__(THREADS, (NBUF == 1 && THREADS <= 384) ? 2 : 1
                     const u32 i0 = ibase | (g << (lowbits + Q2));
                     const u32 row0 = ((a.out_bitrev ? (__brev(i0) >> brsh) : i0) << a.out_sh) + a.out_add;
                     u32 *p = out + (size_t)row0 * a.w + c;
-                    if (a.out_bitrev) {
+                    if (a.skip_store) { u32 acc = 0;
+#pragma unroll
+                        for (u32 m = 0; m < E2; m++) acc ^= x[m];
+                        if (acc == 0x12345678u) p[0] = acc;
+                    } else if (a.out_bitrev) {
 #pragma unroll
                         for (u32 m = 0; m < E2; m++) p[brev_const<Q2>(m) * sstride] = x[m];
                     } else {
@@ -484,7 +490,10 @@ static int32_t launch_fast_rct(p3gpu_ctx *ctx, const PassArgs &a) {
     P3_CHECK(tiles < (1ull << 31), P3GPU_EINVAL, "ntt: grid too large");
     // persistent grid: one CTA per SM (more when the tile is small enough for several to be resident)
     size_t per_sm = std::min<size_t>(NBUF == 1 ? 2048 / THREADS : 2, (227 * 1024) / (smem + 1024));
-    if (THREADS * per_sm * 80 > 65536) per_sm = 65536 / (THREADS * 80);   // register file: ~80 registers per thread
+    cudaFuncAttributes fa;
+    P3_CUDA(cudaFuncGetAttributes(&fa, kern));
+    const size_t by_regs = 65536 / ((size_t)THREADS * (size_t)std::max(fa.numRegs, 16));   // register file of the SM
+    if (per_sm > by_regs) per_sm = by_regs;
     if (per_sm < 1) per_sm = 1;
     const size_t grid = std::min(tiles, per_sm * (size_t)ctx->sm_count);
     kern<<<(unsigned)grid, THREADS, smem, ctx->stream>>>(a);
@@ -496,9 +505,10 @@ template <int F, int R_LOG, int CT_T>
 static int32_t launch_fast_rc(p3gpu_ctx *ctx, const PassArgs &a) {
     static const int threads = env_int("P3GPU_NTT_THREADS", 256);
     if (threads == 512) return launch_fast_rct<F, R_LOG, CT_T, 512, 2>(ctx, a);   // 1 double-buffered CTA per SM
-    // default: 2 single-buffered 256-thread CTAs per SM (one loads its tile while the other computes).  Measured on the
-    // 2^20 x 100 LDE: 1.82 ms, vs 2.17 ms for 1 x 512 double-buffered; block sizes 128/192/320/384 give 1.88/1.82/1.91/1.92 ms —
-    // the kernel is bound by the integer pipes (profiles/README.md), not by the number of resident warps.
+    // default: 2-3 single-buffered 256-thread CTAs per SM (one loads its tile while the others compute).  Measured on the
+    // 2^20 x 100 LDE: 1.82 ms, vs 2.17 ms for 1 x 512 double-buffered; block sizes 128/192/320/384 give 1.88/1.82/1.91/1.92 ms.
+    // Rejected experiments (profiles/README.md): two columns per thread with 64-bit shared accesses (2.01 ms), L2 prefetch
+    // of the next tile (1.99 ms), three passes of 7+7+6 layers with small tiles (3.1 ms).
     return launch_fast_rct<F, R_LOG, CT_T, 256, 1>(ctx, a);
 }
 template <int F, int R_LOG>
@@ -513,6 +523,7 @@ static int32_t launch_fast_r(p3gpu_ctx *ctx, const PassArgs &a) {
 template <int F>
 static int32_t launch_fast(p3gpu_ctx *ctx, const PassArgs &a) {
     switch (a.l1 - a.l0) {
+        case 6: return launch_fast_r<F, 6>(ctx, a);
         case 7: return launch_fast_r<F, 7>(ctx, a);
         case 8: return launch_fast_r<F, 8>(ctx, a);
         case 9: return launch_fast_r<F, 9>(ctx, a);
@@ -524,6 +535,8 @@ static int32_t launch_fast(p3gpu_ctx *ctx, const PassArgs &a) {
 // Prefer exact divisors that keep 16-byte alignment (16, 20, 24 columns = 64/80/96-byte row segments).
 static u32 choose_tile_width(u32 w) {
     if (w <= 24) return w;
+    static const int forced = env_int("P3GPU_NTT_CT", 0);
+    if (forced) return (u32)forced;
     for (u32 ct : {16u, 20u, 24u, 12u})
         if (w % ct == 0) return ct;
     const u32 n = (w + 19) / 20;                 // ~20 columns per tile, nearly equal tiles
@@ -539,13 +552,15 @@ template <int F>
 static int32_t launch_pass(p3gpu_ctx *ctx, PassArgs a, unsigned n_cosets, int main_log_ct) {
     a.n_cosets = n_cosets;
     const int r = a.l1 - a.l0;
-    if (r >= 7 && r <= 10 && !env_int("P3GPU_NTT_GENERIC", 0)) {
+    if (r >= 6 && r <= 10 && !env_int("P3GPU_NTT_GENERIC", 0)) {
         const u32 ct = choose_tile_width(a.w);
         // 16-byte cp.async / TMA bulk stores need every row segment of every tile 16-byte aligned on both sides
         const bool al16 = (a.w % 4 == 0) && (ct % 4 == 0) &&
                           ((reinterpret_cast<uintptr_t>(a.in) | reinterpret_cast<uintptr_t>(a.out)) % 16 == 0) &&
                           ((a.in_stride | a.out_stride) % 4 == 0);
         a.col0 = 0; a.ct = ct; a.n_ctiles = (a.w + ct - 1) / ct; a.vec16 = al16;
+        a.skip_bfly = env_int("P3GPU_NTT_NOBFLY", 0);
+        a.skip_load = env_int("P3GPU_NTT_NOLOAD", 0); a.skip_store = env_int("P3GPU_NTT_NOSTORE", 0);
         return launch_fast<F>(ctx, a);
     }
     const bool aligned = (a.w % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.in) | reinterpret_cast<uintptr_t>(a.out)) % 16 == 0) &&
