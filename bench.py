@@ -286,6 +286,10 @@ def main():
     if world == 1 and not args.no_others:
         others = {}
         k = max(2, min(args.steps, 5))
+        # config 1: Radix2DitParallel forward NTT, BabyBear, 2^16 x 1 (parity case; device time of the single-column transform)
+        x1 = torch.randint(0, BB.P, (1 << 16, 1), device=dev, dtype=torch.int32, generator=g)
+        t, nl = timed(lambda: gpu.dft_batch(BB.id, _lib.DFT, x1), 20, 3)
+        others["config1_dft_bb_2^16x1"] = {"us": t * 1e3, "launches": nl / 20}
         # config 3: MerkleTreeMmcs commit 2^22 x 100 KoalaBear, Poseidon2-16 sponge, cap 0
         xm = torch.randint(0, KB.P, (1 << 22, 100), device=dev, dtype=torch.int32, generator=g)
         t, nl = timed(lambda: gpu.merkle_commit(KB.id, _lib.HASH_POSEIDON2_W16, [xm]), k, 1)

@@ -29,6 +29,14 @@
 
 namespace p3 {
 
+// Phase-breakdown instrumentation (profiles/README.md) is compiled in only with -DP3GPU_NTT_PROFILE; the env switches
+// P3GPU_NTT_NOBFLY / NOLOAD / NOSTORE are ignored by the production build.
+#ifdef P3GPU_NTT_PROFILE
+#define P3_SKIP(flag) (flag)
+#else
+#define P3_SKIP(flag) false
+#endif
+
 struct PassArgs {
     const u32 *in;
     u32 *out;
@@ -315,7 +323,7 @@ __global__ void __launch_bounds__(THREADS, NBUF == 2 ? 1 : (CT_T == 16 && THREAD
             if (t + gridDim.x < total) { issue(t + gridDim.x, buf ^ 1u); cp_async_wait<1>(); }
             else cp_async_wait<0>();
         } else {   // single buffer: other resident CTAs of this SM compute while this one waits for its tile
-            if (!a.skip_load) issue(t, 0);
+            if (!P3_SKIP(a.skip_load)) issue(t, 0);
             cp_async_wait<0>();
         }
         __syncthreads();
@@ -336,7 +344,7 @@ __global__ void __launch_bounds__(THREADS, NBUF == 2 ? 1 : (CT_T == 16 && THREAD
 #pragma unroll
                     for (u32 m = 0; m < E1; m++) x[m] = shoup_mul<F>(x[m], a.scale);
                 }
-                if (!a.skip_bfly) reg_network<F, Q1>(x, tws, 1u);
+                if (!P3_SKIP(a.skip_bfly)) reg_network<F, Q1>(x, tws, 1u);
 #pragma unroll
                 for (u32 m = 0; m < E1; m++) sp[m * gstride] = x[m];
                 c += dc; g += dg;
@@ -356,7 +364,7 @@ __global__ void __launch_bounds__(THREADS, NBUF == 2 ? 1 : (CT_T == 16 && THREAD
                 u32 x[E2];
 #pragma unroll
                 for (u32 m = 0; m < E2; m++) x[m] = sp[m * CT];
-                if (!a.skip_bfly) reg_network<F, Q2>(x, tws, E1 + g);
+                if (!P3_SKIP(a.skip_bfly)) reg_network<F, Q2>(x, tws, E1 + g);
                 if (a.final_reduce) {
 #pragma unroll
                     for (u32 m = 0; m < E2; m++) x[m] = fp_reduce<F>(x[m]);
@@ -365,7 +373,7 @@ __global__ void __launch_bounds__(THREADS, NBUF == 2 ? 1 : (CT_T == 16 && THREAD
                     const u32 i0 = ibase | (g << (lowbits + Q2));
                     const u32 row0 = ((a.out_bitrev ? (__brev(i0) >> brsh) : i0) << a.out_sh) + a.out_add;
                     u32 *p = out + (size_t)row0 * a.w + c;
-                    if (a.skip_store) { u32 acc = 0;
+                    if (P3_SKIP(a.skip_store)) { u32 acc = 0;
 #pragma unroll
                         for (u32 m = 0; m < E2; m++) acc ^= x[m];
                         if (acc == 0x12345678u) p[0] = acc;
@@ -485,14 +493,22 @@ static int32_t launch_fast_rct(p3gpu_ctx *ctx, const PassArgs &a) {
     const size_t smem = NBUF * buf_words * 4 + NBUF * ((size_t)1 << R_LOG) * sizeof(uint2);
     auto kern = ntt_pass_fast_kernel<F, R_LOG, CT_T, THREADS, NBUF>;
     P3_CHECK(smem <= 227 * 1024, P3GPU_EINVAL, "ntt: tile does not fit shared memory");
-    if (smem > 48 * 1024) P3_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static size_t smem_set[64] = {0};   // per instantiation and device: raise the dynamic shared memory limit once per size
+    if (smem > 48 * 1024 && smem > smem_set[ctx->device & 63]) {
+        P3_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_set[ctx->device & 63] = smem;
+    }
     const size_t tiles = ((size_t)1 << (a.log_n - R_LOG)) * a.n_ctiles * a.n_cosets;
     P3_CHECK(tiles < (1ull << 31), P3GPU_EINVAL, "ntt: grid too large");
     // persistent grid: one CTA per SM (more when the tile is small enough for several to be resident)
     size_t per_sm = std::min<size_t>(NBUF == 1 ? 2048 / THREADS : 2, (227 * 1024) / (smem + 1024));
-    cudaFuncAttributes fa;
-    P3_CUDA(cudaFuncGetAttributes(&fa, kern));
-    const size_t by_regs = 65536 / ((size_t)THREADS * (size_t)std::max(fa.numRegs, 16));   // register file of the SM
+    static int num_regs = 0;   // per instantiation; benign race (same value)
+    if (num_regs == 0) {
+        cudaFuncAttributes fa;
+        P3_CUDA(cudaFuncGetAttributes(&fa, kern));
+        num_regs = std::max(fa.numRegs, 16);
+    }
+    const size_t by_regs = 65536 / ((size_t)THREADS * (size_t)num_regs);   // register file of the SM
     if (per_sm > by_regs) per_sm = by_regs;
     if (per_sm < 1) per_sm = 1;
     const size_t grid = std::min(tiles, per_sm * (size_t)ctx->sm_count);
