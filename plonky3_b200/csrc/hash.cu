@@ -230,51 +230,75 @@ __global__ void __launch_bounds__(128) poseidon2_compress_kernel(const u32 *in, 
 // =================================================================================================
 // Keccak-f[1600]
 // =================================================================================================
-__constant__ u64 KECCAK_RC[24] = {
-    0x0000000000000001ULL, 0x0000000000008082ULL, 0x800000000000808aULL, 0x8000000080008000ULL, 0x000000000000808bULL,
-    0x0000000080000001ULL, 0x8000000080008081ULL, 0x8000000000008009ULL, 0x000000000000008aULL, 0x0000000000000088ULL,
-    0x0000000080008009ULL, 0x000000008000000aULL, 0x000000008000808bULL, 0x800000000000008bULL, 0x8000000000008089ULL,
-    0x8000000000008003ULL, 0x8000000000008002ULL, 0x8000000000000080ULL, 0x000000000000800aULL, 0x800000008000000aULL,
-    0x8000000080008081ULL, 0x8000000000008080ULL, 0x0000000080000001ULL, 0x8000000080008008ULL};
+// The state is kept as 25 (lo, hi) pairs of 32-bit registers: every 64-bit rotation is two funnel shifts (SHF), theta's
+// column parity + application and chi are single 3-input LOP3s, so a round is exactly 122 LOP3 + 58 SHF and no register
+// moves (the compiler's 64-bit version needed 162 LOP3 + 52 SHF + 46 moves).  All of it runs on the ALU pipe: the kernel is
+// bound by that pipe (ncu: 98 % busy).  The (lo, hi) split also matches the leaf packing, which pairs consecutive u32
+// field elements into one u64 word (field/src/integers.rs:494-509): lo = first element, hi = second.
+__constant__ u32 KECCAK_RC_LO[24] = {0x00000001u, 0x00008082u, 0x0000808au, 0x80008000u, 0x0000808bu, 0x80000001u, 0x80008081u, 0x00008009u,
+                                      0x0000008au, 0x00000088u, 0x80008009u, 0x8000000au, 0x8000808bu, 0x0000008bu, 0x00008089u, 0x00008003u,
+                                      0x00008002u, 0x00000080u, 0x0000800au, 0x8000000au, 0x80008081u, 0x00008080u, 0x80000001u, 0x80008008u};
+__constant__ u32 KECCAK_RC_HI[24] = {0x00000000u, 0x00000000u, 0x80000000u, 0x80000000u, 0x00000000u, 0x00000000u, 0x80000000u, 0x80000000u,
+                                      0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x80000000u, 0x80000000u, 0x80000000u,
+                                      0x80000000u, 0x80000000u, 0x00000000u, 0x80000000u, 0x80000000u, 0x80000000u, 0x00000000u, 0x80000000u};
 
-__device__ __forceinline__ u64 rotl64(u64 x, int r) { return (x << r) | (x >> (64 - r)); }
+// 64-bit rotate-left of (lo, hi) by the compile-time constant R
+template <int R> __device__ __forceinline__ void rot64(u32 lo, u32 hi, u32 &olo, u32 &ohi) {
+    if constexpr (R == 0) { olo = lo; ohi = hi; }
+    else if constexpr (R == 32) { olo = hi; ohi = lo; }
+    else if constexpr (R < 32) { olo = __funnelshift_l(hi, lo, R); ohi = __funnelshift_l(lo, hi, R); }
+    else { olo = __funnelshift_l(lo, hi, R - 32); ohi = __funnelshift_l(hi, lo, R - 32); }
+}
 
-__device__ __forceinline__ void keccak_f(u64 (&a)[25]) {
+struct KState { u32 lo[25], hi[25]; };
+
+__device__ __forceinline__ void keccak_f(KState &s) {
+    u32 (&al)[25] = s.lo;
+    u32 (&ah)[25] = s.hi;
 #pragma unroll 1
     for (int round = 0; round < 24; round++) {
-        u64 c[5], d[5];
+        u32 cl[5], ch[5], rl[5], rh[5];
 #pragma unroll
-        for (int x = 0; x < 5; x++) c[x] = a[x] ^ a[x + 5] ^ a[x + 10] ^ a[x + 15] ^ a[x + 20];
+        for (int x = 0; x < 5; x++) {
+            cl[x] = al[x] ^ al[x + 5] ^ al[x + 10] ^ al[x + 15] ^ al[x + 20];
+            ch[x] = ah[x] ^ ah[x + 5] ^ ah[x + 10] ^ ah[x + 15] ^ ah[x + 20];
+        }
 #pragma unroll
-        for (int x = 0; x < 5; x++) d[x] = c[(x + 4) % 5] ^ rotl64(c[(x + 1) % 5], 1);
-#pragma unroll
-        for (int i = 0; i < 25; i++) a[i] ^= d[i % 5];
-        // rho + pi
-        u64 b[25];
-        b[0] = a[0];
-        b[10] = rotl64(a[1], 1);   b[20] = rotl64(a[2], 62);  b[5] = rotl64(a[3], 28);   b[15] = rotl64(a[4], 27);
-        b[16] = rotl64(a[5], 36);  b[1] = rotl64(a[6], 44);   b[11] = rotl64(a[7], 6);   b[21] = rotl64(a[8], 55);
-        b[6] = rotl64(a[9], 20);   b[7] = rotl64(a[10], 3);   b[17] = rotl64(a[11], 10); b[2] = rotl64(a[12], 43);
-        b[12] = rotl64(a[13], 25); b[22] = rotl64(a[14], 39); b[23] = rotl64(a[15], 41); b[8] = rotl64(a[16], 45);
-        b[18] = rotl64(a[17], 15); b[3] = rotl64(a[18], 21);  b[13] = rotl64(a[19], 8);  b[14] = rotl64(a[20], 18);
-        b[24] = rotl64(a[21], 2);  b[9] = rotl64(a[22], 61);  b[19] = rotl64(a[23], 56); b[4] = rotl64(a[24], 14);
+        for (int x = 0; x < 5; x++) rot64<1>(cl[x], ch[x], rl[x], rh[x]);
+        u32 bl[25], bh[25];
+        // theta + rho + pi: b[pi(i)] = rotl(a[i] ^ C[x-1] ^ rotl(C[x+1], 1), rho(i))
+#define P3_TH(i, R, dst)                                                                             \
+    rot64<R>(al[i] ^ cl[((i) % 5 + 4) % 5] ^ rl[((i) % 5 + 1) % 5], ah[i] ^ ch[((i) % 5 + 4) % 5] ^ rh[((i) % 5 + 1) % 5], \
+             bl[dst], bh[dst])
+        P3_TH(0, 0, 0);
+        P3_TH(1, 1, 10);   P3_TH(2, 62, 20);  P3_TH(3, 28, 5);   P3_TH(4, 27, 15);
+        P3_TH(5, 36, 16);  P3_TH(6, 44, 1);   P3_TH(7, 6, 11);   P3_TH(8, 55, 21);
+        P3_TH(9, 20, 6);   P3_TH(10, 3, 7);   P3_TH(11, 10, 17); P3_TH(12, 43, 2);
+        P3_TH(13, 25, 12); P3_TH(14, 39, 22); P3_TH(15, 41, 23); P3_TH(16, 45, 8);
+        P3_TH(17, 15, 18); P3_TH(18, 21, 3);  P3_TH(19, 8, 13);  P3_TH(20, 18, 14);
+        P3_TH(21, 2, 24);  P3_TH(22, 61, 9);  P3_TH(23, 56, 19); P3_TH(24, 14, 4);
+#undef P3_TH
 #pragma unroll
         for (int y = 0; y < 5; y++)
 #pragma unroll
-            for (int x = 0; x < 5; x++) a[x + 5 * y] = b[x + 5 * y] ^ (~b[(x + 1) % 5 + 5 * y] & b[(x + 2) % 5 + 5 * y]);
-        a[0] ^= KECCAK_RC[round];
+            for (int x = 0; x < 5; x++) {
+                al[x + 5 * y] = bl[x + 5 * y] ^ (~bl[(x + 1) % 5 + 5 * y] & bl[(x + 2) % 5 + 5 * y]);
+                ah[x + 5 * y] = bh[x + 5 * y] ^ (~bh[(x + 1) % 5 + 5 * y] & bh[(x + 2) % 5 + 5 * y]);
+            }
+        al[0] ^= KECCAK_RC_LO[round];
+        ah[0] ^= KECCAK_RC_HI[round];
     }
 }
 
 __global__ void __launch_bounds__(128) keccak_f_kernel(u64 *states, size_t n) {
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= n) return;
-    u64 a[25];
+    KState s;
 #pragma unroll
-    for (int i = 0; i < 25; i++) a[i] = states[idx * 25 + i];
-    keccak_f(a);
+    for (int i = 0; i < 25; i++) { const u64 v = states[idx * 25 + i]; s.lo[i] = (u32)v; s.hi[i] = (u32)(v >> 32); }
+    keccak_f(s);
 #pragma unroll
-    for (int i = 0; i < 25; i++) states[idx * 25 + i] = a[i];
+    for (int i = 0; i < 25; i++) states[idx * 25 + i] = (u64)s.lo[i] | ((u64)s.hi[i] << 32);
 }
 
 // leaf = SerializingHasher<PaddingFreeSponge<KeccakF,25,17,4>>: u32 pairs -> u64 words over the concatenated row stream
@@ -282,9 +306,9 @@ __global__ void __launch_bounds__(128) keccak_f_kernel(u64 *states, size_t n) {
 __global__ void __launch_bounds__(128) keccak_leaf_kernel(const __grid_constant__ LeafArgs a) {
     const size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= a.height) return;
-    u64 s[25];
+    KState s;
 #pragma unroll
-    for (int i = 0; i < 25; i++) s[i] = 0;
+    for (int i = 0; i < 25; i++) { s.lo[i] = 0; s.hi[i] = 0; }
     const bool single = (a.n_mats == 1);
     const u32 w0 = a.width[0];
     const u32 *row0 = a.ptr[0] + r * w0;
@@ -295,39 +319,43 @@ __global__ void __launch_bounds__(128) keccak_leaf_kernel(const __grid_constant_
 #pragma unroll
             for (int i = 0; i < 17; i++) {
                 const u32 e = c0 + 2 * i;
-                if (e < w0) s[i] = (u64)__ldg(row0 + e) | (e + 1 < w0 ? ((u64)__ldg(row0 + e + 1) << 32) : 0ull);
+                if (e < w0) { s.lo[i] = __ldg(row0 + e); s.hi[i] = e + 1 < w0 ? __ldg(row0 + e + 1) : 0u; }
             }
             c0 += 34;
         } else {
 #pragma unroll
             for (int i = 0; i < 17; i++) {
                 if (cur.more()) {
-                    const u64 lo = cur.next();
-                    const u64 hi = cur.more() ? (u64)cur.next() : 0ull;
-                    s[i] = lo | (hi << 32);
+                    s.lo[i] = cur.next();
+                    s.hi[i] = cur.more() ? cur.next() : 0u;
                 }
             }
         }
         keccak_f(s);
     }
-    u64 *o = reinterpret_cast<u64 *>(a.out + r * 8);
-    o[0] = s[0]; o[1] = s[1]; o[2] = s[2]; o[3] = s[3];
+    uint4 *o = reinterpret_cast<uint4 *>(a.out + r * 8);
+    o[0] = make_uint4(s.lo[0], s.hi[0], s.lo[1], s.hi[1]);
+    o[1] = make_uint4(s.lo[2], s.hi[2], s.lo[3], s.hi[3]);
 }
 
 // node = CompressionFunctionFromHasher<sponge,2,4>: 8 words < rate 17 -> exactly one permutation (compression.rs:60-70)
 __global__ void __launch_bounds__(128) keccak_compress_kernel(const u32 *in, const u32 *inj, size_t inj_h, u32 *out, size_t n, int rmode) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    u64 s[25];
+    KState s;
 #pragma unroll
-    for (int j = 0; j < 25; j++) s[j] = 0;
-    const u64 *l = reinterpret_cast<const u64 *>(rmode == 0 ? in + 16 * i : out + 8 * i);
-    s[0] = l[0]; s[1] = l[1]; s[2] = l[2]; s[3] = l[3];
-    if (rmode == 0) { s[4] = l[4]; s[5] = l[5]; s[6] = l[6]; s[7] = l[7]; }
-    else if (i < inj_h) { const u64 *rp = reinterpret_cast<const u64 *>(inj + 8 * i); s[4] = rp[0]; s[5] = rp[1]; s[6] = rp[2]; s[7] = rp[3]; }
+    for (int j = 0; j < 25; j++) { s.lo[j] = 0; s.hi[j] = 0; }
+    const uint4 *l = reinterpret_cast<const uint4 *>(rmode == 0 ? in + 16 * i : out + 8 * i);
+    const uint4 a0 = l[0], a1 = l[1];
+    s.lo[0] = a0.x; s.hi[0] = a0.y; s.lo[1] = a0.z; s.hi[1] = a0.w; s.lo[2] = a1.x; s.hi[2] = a1.y; s.lo[3] = a1.z; s.hi[3] = a1.w;
+    uint4 b0 = make_uint4(0, 0, 0, 0), b1 = b0;
+    if (rmode == 0) { b0 = l[2]; b1 = l[3]; }
+    else if (i < inj_h) { const uint4 *rp = reinterpret_cast<const uint4 *>(inj + 8 * i); b0 = rp[0]; b1 = rp[1]; }
+    s.lo[4] = b0.x; s.hi[4] = b0.y; s.lo[5] = b0.z; s.hi[5] = b0.w; s.lo[6] = b1.x; s.hi[6] = b1.y; s.lo[7] = b1.z; s.hi[7] = b1.w;
     keccak_f(s);
-    u64 *o = reinterpret_cast<u64 *>(out + 8 * i);
-    o[0] = s[0]; o[1] = s[1]; o[2] = s[2]; o[3] = s[3];
+    uint4 *o = reinterpret_cast<uint4 *>(out + 8 * i);
+    o[0] = make_uint4(s.lo[0], s.hi[0], s.lo[1], s.hi[1]);
+    o[1] = make_uint4(s.lo[2], s.hi[2], s.lo[3], s.hi[3]);
 }
 
 // =================================================================================================
