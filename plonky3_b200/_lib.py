@@ -3,10 +3,12 @@ device is present, importing callers get a hard error."""
 from __future__ import annotations
 
 import ctypes as C
+import os
 import pathlib
 
 _HERE = pathlib.Path(__file__).resolve().parent
-LIB_PATH = _HERE / "libp3gpu.so"
+# P3GPU_LIB selects another build of the same library (e.g. the -DP3GPU_NTT_PROFILE instrumented one); never a fallback
+LIB_PATH = pathlib.Path(os.environ["P3GPU_LIB"]) if os.environ.get("P3GPU_LIB") else _HERE / "libp3gpu.so"
 
 BABY_BEAR, KOALA_BEAR = 0, 1
 DFT, IDFT, COSET_DFT, COSET_IDFT = 0, 1, 2, 3

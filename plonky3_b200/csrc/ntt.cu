@@ -25,6 +25,8 @@
 #include <cstdlib>
 #include <cstring>
 
+#include <cuda.h>   // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint, no libcuda link)
+
 #include "common.h"
 
 namespace p3 {
@@ -37,6 +39,11 @@ namespace p3 {
 #define P3_SKIP(flag) false
 #endif
 
+static int env_int(const char *name, int dflt) {
+    const char *s = getenv(name);
+    return s ? atoi(s) : dflt;
+}
+
 struct PassArgs {
     const u32 *in;
     u32 *out;
@@ -48,6 +55,11 @@ struct PassArgs {
     u32 vec16;     // fast kernel: row segments are 16-byte aligned (cp.async 16)
     u32 skip_load, skip_store;  // profiling experiments only
     u32 skip_bfly; // profiling experiment only (P3GPU_NTT_NOBFLY=1): move the data, skip the butterflies
+    u32 wc;                    // pipelined kernel: columns of this launch (<= w = row pitch of the dense layout)
+    u32 in_tiled, out_tiled;   // pipelined kernel: intermediate buffers in column-tile-major layout (see lde_tiled_impl)
+    u32 in_blocks;             // pipelined kernel, tiled input: 2^log_n-row blocks per column tile (cosets)
+    u32 n_items, csplit, tpi;  // pipelined kernel: work items = (row tile, coset) units x csplit column chunks of tpi tiles
+    unsigned long long *prof;  // profiling build only: per CTA/tile phase timestamps (P3GPU_NTT_PROFBUF)
     int log_n, l0, l1;
     const uint2 *tw;  // heap-ordered twiddles of coset 0
     int in_bitrev, out_bitrev;
@@ -314,19 +326,32 @@ __global__ void __launch_bounds__(THREADS, NBUF == 2 ? 1 : (CT_T == 16 && THREAD
 
     u32 t = blockIdx.x;
     if (t >= total) return;
+#ifdef P3GPU_NTT_PROFILE
+    // 8 slots per (CTA, tile < 16): smid, t_start, t_issued, t_loaded, t_step1, t_step2 (globaltimer ns)
+#define P3_STAMP(slot) do { if (a.prof && threadIdx.x == 0 && k < 16) { unsigned long long ts_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ts_)); \
+        a.prof[((size_t)blockIdx.x * 16 + k) * 8 + (slot)] = ts_; } } while (0)
+#else
+#define P3_STAMP(slot) do { } while (0)
+#endif
     if (shared_tw && a.n_cosets == 1) issue_twiddles(0, 0, tws0);   // once per CTA, lands with the first tile's group
     if (NBUF == 2) issue(t, 0);
     for (u32 k = 0; t < total; t += gridDim.x, k++) {
         const u32 buf = NBUF == 2 ? (k & 1u) : 0u;
         __syncthreads();   // every warp is done reading the buffer that is refilled next
+#ifdef P3GPU_NTT_PROFILE
+        if (a.prof && threadIdx.x == 0 && k < 16) { u32 sm_; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm_)); a.prof[((size_t)blockIdx.x * 16 + k) * 8] = sm_; }
+#endif
+        P3_STAMP(1);
         if (NBUF == 2) {
             if (t + gridDim.x < total) { issue(t + gridDim.x, buf ^ 1u); cp_async_wait<1>(); }
             else cp_async_wait<0>();
         } else {   // single buffer: other resident CTAs of this SM compute while this one waits for its tile
             if (!P3_SKIP(a.skip_load)) issue(t, 0);
+            P3_STAMP(2);
             cp_async_wait<0>();
         }
         __syncthreads();
+        P3_STAMP(3);
         u32 *data = data0 + buf * buf_words;
         const uint2 *tws = (shared_tw && a.n_cosets == 1) ? tws0 : tws0 + buf * R;  // NBUF == 1: buf == 0
         u32 coset, col, cw, T, ibase;
@@ -352,6 +377,7 @@ __global__ void __launch_bounds__(THREADS, NBUF == 2 ? 1 : (CT_T == 16 && THREAD
             }
         }
         __syncthreads();
+        P3_STAMP(4);
         // ---- step 2: item (g, c) holds local rows g*E2 + m, m < E2
         {
             u32 *out = a.out + (size_t)coset * a.out_stride + col;
@@ -388,6 +414,237 @@ __global__ void __launch_bounds__(THREADS, NBUF == 2 ? 1 : (CT_T == 16 && THREAD
                 c += dc; g += dg;
                 if (c >= cw) { c -= cw; g++; }
             }
+        }
+        P3_STAMP(5);
+    }
+}
+
+// ---- pipelined path: TMA tile loads + warp-specialised consumer groups -------------------------------------------
+// The cp.async kernel above spends ~5 of its ~17 us per tile issuing and waiting for its own loads (LDGSTS issue is
+// back-pressured by HBM latency: ~20 KB in flight per CTA, tools/ntt_timeline.py), and only 2-3 CTAs fit an SM.  This kernel
+// keeps ONE CTA per SM and decouples the two jobs:
+//   * a producer lane walks the CTA's tile sequence and issues ONE 5-D tiled TMA copy per tile (cp.async.bulk.tensor) into a
+//     ring of NSTAGE shared-memory stages, plus the tile row's 2^r - 1 twiddles as 1-D bulk copies; completion is signalled
+//     on mbarriers, so up to NSTAGE - NGROUP tiles (~34 KB each) are always in flight per SM at zero issue cost;
+//   * NGROUP independent consumer groups (GTHREADS threads, own named barrier) each take every NGROUP-th tile through the same
+//     two register networks as above and release the stage as soon as their last shared-memory read is done.
+// Tiles are 2^r rows x 8 columns (32-byte row segments = one sector).  The TMA box is (8 cols, GS + 1, NG): asking for one
+// row more than the tensor has in the "row within group" dimension makes the copy engine zero-fill a padding row per group,
+// which is exactly the skew (group stride = 8 mod 32 words) that keeps both register-network access patterns bank-conflict
+// free; no other padding mechanism exists for a dense TMA box.
+// A CTA processes all column tiles of one (row tile, coset) unit back to back, so the unit's twiddles are staged once and
+// neighbouring 32-byte segments of the same rows are requested within microseconds of each other (L2/DRAM page locality).
+// PERM = the pass reads its rows through the bit-reversal map (first forward pass of the LDE): the tile is then a CONTIGUOUS
+// block of rows holding local row rho at position bitrev_r(rho); the two steps simply swap their shared-memory access shapes.
+__device__ __forceinline__ void mbar_init(u32 bar, u32 count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
+__device__ __forceinline__ void mbar_wait(u32 bar, u32 parity) {
+    u32 done = 0;
+    while (!done)
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(u32 bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ void mbar_arrive_n(u32 bar, u32 n) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(n) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(u32 bar, u32 bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory"); }
+
+template <int F, int R_LOG, bool PERM, int NSTAGE, int NGROUP, int GTHREADS>
+__global__ void __launch_bounds__(NGROUP * GTHREADS + 32, 1) ntt_pass_pipe_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ PassArgs a) {
+    constexpr u32 CT = 8;
+    constexpr int Q2 = (R_LOG + 1) / 2, Q1 = R_LOG - Q2;
+    constexpr u32 E1 = 1u << Q1, E2 = 1u << Q2, R = 1u << R_LOG;
+    constexpr u32 GS = PERM ? E1 : E2, NG = PERM ? E2 : E1;   // rows per group, groups per tile (see above)
+    constexpr u32 gstride = (GS + 1) * CT;
+    constexpr u32 STAGE_WORDS = NG * gstride;
+    constexpr u32 BOX_BYTES = STAGE_WORDS * 4;
+    static_assert(BOX_BYTES % 128 == 0, "stage alignment");
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    u32 *stages = reinterpret_cast<u32 *>(smem_raw);
+    uint2 *tws0 = reinterpret_cast<uint2 *>(smem_raw + (size_t)NSTAGE * BOX_BYTES);
+    const u32 bar0 = (u32)__cvta_generic_to_shared(smem_raw + (size_t)NSTAGE * BOX_BYTES + 2 * R * sizeof(uint2));
+    // barrier slots (8 bytes each): full[s] = s, empty[s] = NSTAGE + s, twfull[b] = 2 NSTAGE + b, twempty[b] = 2 NSTAGE + 2 + b
+    auto full_bar = [&](u32 s) { return bar0 + 8u * s; };
+    auto empty_bar = [&](u32 s) { return bar0 + 8u * (NSTAGE + s); };
+    auto twfull_bar = [&](u32 b) { return bar0 + 8u * (2 * NSTAGE + b); };
+    auto twempty_bar = [&](u32 b) { return bar0 + 8u * (2 * NSTAGE + 2 + b); };
+
+    if (threadIdx.x == 0) {
+        for (u32 s = 0; s < NSTAGE; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), GTHREADS); }
+        for (u32 b = 0; b < 2; b++) { mbar_init(twfull_bar(b), 1); mbar_init(twempty_bar(b), a.tpi * GTHREADS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const int lowbits = a.log_n - a.l1;
+    const int brsh = 32 - a.log_n;
+    auto decode = [&](u32 it, u32 &coset, u32 &L, u32 &T, u32 &ct0, u32 &ct1) {
+        const u32 unit = it / a.csplit, chunk = it - unit * a.csplit;
+        coset = unit % a.n_cosets;
+        const u32 tile = unit / a.n_cosets;
+        L = tile & ((1u << lowbits) - 1u);
+        T = tile >> lowbits;
+        ct0 = chunk * a.tpi;
+        ct1 = min(ct0 + a.tpi, a.n_ctiles);
+    };
+
+    if (threadIdx.x >= NGROUP * GTHREADS) {
+        // ---------------- producer ----------------
+        if ((threadIdx.x & 31u) != 0) return;
+        u32 q = 0, ui = 0;
+        for (u32 it = blockIdx.x; it < a.n_items; it += gridDim.x, ui++) {
+            u32 coset, L, T, ct0, ct1;
+            decode(it, coset, L, T, ct0, ct1);
+            const u32 b = ui & 1u, ph = (ui >> 1) & 1u;
+            mbar_wait(twempty_bar(b), ph ^ 1u);   // every tile of unit ui-2 is done with this twiddle buffer
+            if (ct1 - ct0 < a.tpi) mbar_arrive_n(twempty_bar(b), (a.tpi - (ct1 - ct0)) * GTHREADS);   // short last chunk
+            {
+                const uint2 *tw = a.tw + (size_t)coset * a.tw_stride;
+                uint2 *tws = tws0 + b * R;
+                tws[1] = tw[((size_t)1 << a.l0) + T];   // layer lam = 0 has a single 8-byte entry: too small for a bulk copy
+                mbar_expect_tx(twfull_bar(b), 8u * (R - 2u));
+#pragma unroll 1
+                for (int lam = 1; lam < R_LOG; lam++) {
+                    const uint2 *src = tw + ((size_t)1 << (a.l0 + lam)) + ((size_t)T << lam);
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                 ::"r"((u32)__cvta_generic_to_shared(tws + (1u << lam))), "l"(src), "r"(8u << lam), "r"(twfull_bar(b)) : "memory");
+                }
+            }
+            // tensor coordinates: (column, 0, 0, c3, c4); see make_pass_tensor_map
+            // tiled input: column tile ct, block cb is the 8-column matrix number ct * in_blocks + cb (blocks fold into dim 4)
+            const u32 in_block = (a.in_tiled ? a.in_blocks > 1 : a.in_stride != 0) ? coset : 0u;
+            const int blk_sh = PERM ? lowbits : a.l0;   // dim-4 coordinates per 2^log_n-row block
+            const int c3 = PERM ? 0 : (int)L;
+            const int c4 = (PERM ? (lowbits ? (int)(__brev(L) >> (32 - lowbits)) : 0) : (int)T) + (int)(in_block << blk_sh);
+            for (u32 ct = ct0; ct < ct1; ct++, q++) {
+                const u32 s = q % NSTAGE, k = q / NSTAGE;
+                mbar_wait(empty_bar(s), (k & 1u) ^ 1u);
+                mbar_expect_tx(full_bar(s), BOX_BYTES);
+                const int cc0 = a.in_tiled ? 0 : (int)(ct * CT);
+                const int cc4 = a.in_tiled ? c4 + (int)((ct * a.in_blocks) << blk_sh) : c4;
+                asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
+                             ::"r"((u32)__cvta_generic_to_shared(stages + (size_t)s * STAGE_WORDS)), "l"(reinterpret_cast<unsigned long long>(&tmap)),
+                               "r"(cc0), "r"(0), "r"(0), "r"(c3), "r"(cc4), "r"(full_bar(s)) : "memory");
+            }
+        }
+        return;
+    }
+
+    // ---------------- consumers ----------------
+    const u32 gid = threadIdx.x / GTHREADS, tg = threadIdx.x - gid * GTHREADS;
+    u32 q = 0, ui = 0;
+#ifdef P3GPU_NTT_PROFILE
+    u32 kk = 0;   // tiles taken by this group; 8 slots per (CTA, group, tile < 16): smid, t_start, t_full, t_step1, t_step2
+#define P3_GSTAMP(slot) do { if (a.prof && tg == 0 && kk < 16) { unsigned long long ts_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ts_)); \
+        a.prof[(((size_t)blockIdx.x * NGROUP + gid) * 16 + kk) * 8 + (slot)] = ts_; } } while (0)
+#else
+#define P3_GSTAMP(slot) do { } while (0)
+#endif
+    for (u32 it = blockIdx.x; it < a.n_items; it += gridDim.x, ui++) {
+        u32 coset, L, T, ct0, ct1;
+        decode(it, coset, L, T, ct0, ct1);
+        const u32 b = ui & 1u, ph = (ui >> 1) & 1u;
+        const uint2 *tws = tws0 + b * R;
+        const u32 ibase = (a.l0 == 0 ? 0u : (T << (a.log_n - a.l0))) | L;
+        bool tw_ready = false;
+        for (u32 ct = ct0; ct < ct1; ct++, q++) {
+            if (q % NGROUP != gid) continue;
+            const u32 s = q % NSTAGE, k = q / NSTAGE;
+            const u32 col = ct * CT, cw = min(CT, a.wc - col);
+            u32 *data = stages + (size_t)s * STAGE_WORDS;
+            P3_GSTAMP(1);
+            mbar_wait(full_bar(s), k & 1u);
+            if (!tw_ready) { mbar_wait(twfull_bar(b), ph); tw_ready = true; }
+            P3_GSTAMP(2);
+            const u32 dg = GTHREADS / cw, dc = GTHREADS - dg * cw;
+            // ---- step 1 (in place): E1 values per item, Q1 layers
+            {
+                u32 g = tg / cw, c = tg - g * cw;
+                for (; g < E2; ) {
+                    u32 x[E1];
+                    if (!PERM) {
+                        u32 *sp = data + g * CT + c;           // local rows g + m*E2
+#pragma unroll
+                        for (u32 m = 0; m < E1; m++) x[m] = sp[m * gstride];
+                        if (a.has_scale) {
+#pragma unroll
+                            for (u32 m = 0; m < E1; m++) x[m] = shoup_mul<F>(x[m], a.scale);
+                        }
+                        reg_network<F, Q1>(x, tws, 1u);
+#pragma unroll
+                        for (u32 m = 0; m < E1; m++) sp[m * gstride] = x[m];
+                    } else {
+                        u32 *sp = data + g * gstride + c;      // g = gamma: local rows bitrev_Q2(gamma) + m*E2 sit in group gamma
+#pragma unroll
+                        for (u32 m = 0; m < E1; m++) x[m] = sp[brev_const<Q1>(m) * CT];
+                        if (a.has_scale) {
+#pragma unroll
+                            for (u32 m = 0; m < E1; m++) x[m] = shoup_mul<F>(x[m], a.scale);
+                        }
+                        reg_network<F, Q1>(x, tws, 1u);
+#pragma unroll
+                        for (u32 m = 0; m < E1; m++) sp[brev_const<Q1>(m) * CT] = x[m];
+                    }
+                    c += dc; g += dg;
+                    if (c >= cw) { c -= cw; g++; }
+                }
+            }
+            asm volatile("bar.sync %0, %1;" ::"r"(gid + 1u), "r"((u32)GTHREADS) : "memory");
+            P3_GSTAMP(3);
+            // ---- step 2: E2 values per item, Q2 layers, results straight to global memory
+            {
+                // dense output: row pitch w, this tile at column col of coset block `coset`;
+                // tiled output: 8-column matrix number ct * n_cosets + coset, row pitch 8
+                const u32 ow = a.out_tiled ? CT : a.w;
+                u32 *out = a.out_tiled ? a.out + ((((size_t)ct * a.n_cosets + coset) << a.log_n) << 3) : a.out + (size_t)coset * a.out_stride + col;
+                const size_t sstride = ((size_t)(a.out_bitrev ? (1u << (a.l0 + Q1)) : (1u << lowbits)) << a.out_sh) * ow;
+                u32 g = tg / cw, c = tg - g * cw;
+                bool released = false;
+                for (; g < E1; ) {
+                    u32 x[E2];
+                    u32 gg;   // item = local rows gg*E2 + m
+                    if (!PERM) {
+                        gg = g;
+                        const u32 *sp = data + g * gstride + c;
+#pragma unroll
+                        for (u32 m = 0; m < E2; m++) x[m] = sp[m * CT];
+                    } else {
+                        gg = __brev(g) >> (32 - Q1);
+                        const u32 *sp = data + g * CT + c;
+#pragma unroll
+                        for (u32 m = 0; m < E2; m++) x[m] = sp[brev_const<Q2>(m) * gstride];
+                    }
+                    u32 gn = g + dg, cn = c + dc;
+                    if (cn >= cw) { cn -= cw; gn++; }
+                    if (gn >= E1) {   // last shared-memory read of this thread for this stage: hand it back to the producer
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        mbar_arrive(empty_bar(s));
+                        released = true;
+                    }
+                    reg_network<F, Q2>(x, tws, E1 + gg);
+                    if (a.final_reduce) {
+#pragma unroll
+                        for (u32 m = 0; m < E2; m++) x[m] = fp_reduce<F>(x[m]);
+                    }
+                    const u32 i0 = ibase | (gg << (lowbits + Q2));
+                    const u32 row0 = ((a.out_bitrev ? (__brev(i0) >> brsh) : i0) << a.out_sh) + a.out_add;
+                    u32 *p = out + (size_t)row0 * ow + c;
+                    if (a.out_bitrev) {
+#pragma unroll
+                        for (u32 m = 0; m < E2; m++) p[brev_const<Q2>(m) * sstride] = x[m];
+                    } else {
+#pragma unroll
+                        for (u32 m = 0; m < E2; m++) p[m * sstride] = x[m];
+                    }
+                    g = gn; c = cn;
+                }
+                if (!released) {   // threads without a step-2 item (ragged tile)
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    mbar_arrive(empty_bar(s));
+                }
+            }
+            mbar_arrive(twempty_bar(b));
+            P3_GSTAMP(4);
+#ifdef P3GPU_NTT_PROFILE
+            kk++;
+#endif
         }
     }
 }
@@ -461,11 +718,6 @@ static int32_t get_twiddles(p3gpu_ctx *ctx, int log_n, int added_bits, u32 shift
     else ctx->twiddle_bytes += n_cosets * N * sizeof(uint2);
     *out = Z;
     return P3GPU_OK;
-}
-
-static int env_int(const char *name, int dflt) {
-    const char *s = getenv(name);
-    return s ? atoi(s) : dflt;
 }
 
 template <int F, int LOG_CT, bool VEC>
@@ -547,6 +799,111 @@ static int32_t launch_fast(p3gpu_ctx *ctx, const PassArgs &a) {
     }
 }
 
+// ---- pipelined kernel: host side -------------------------------------------------------------------------------
+typedef CUresult (*TensorMapEncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                      const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                      CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static TensorMapEncodeFn tensor_map_encoder() {
+    static TensorMapEncodeFn fn = []() -> TensorMapEncodeFn {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess || qres != cudaDriverEntryPointSuccess)
+            return nullptr;
+        return reinterpret_cast<TensorMapEncodeFn>(p);
+    }();
+    return fn;
+}
+
+// 5-D view of the pass input for ntt_pass_pipe_kernel: (column, row-in-group, group, L, T) with the tile's local row
+// rho = group * GS + row-in-group at global row  T * 2^(n-l0) + rho * 2^lowbits + L   (PERM: block * 2^r + position).
+static int32_t make_pass_tensor_map(const PassArgs &a, bool perm, CUtensorMap *tm) {
+    TensorMapEncodeFn enc = tensor_map_encoder();
+    P3_CHECK(enc != nullptr, P3GPU_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    const int r = a.l1 - a.l0, q2 = (r + 1) / 2, q1 = r - q2, lowbits = a.log_n - a.l1;
+    const cuuint64_t pitch = a.in_tiled ? 32 : (cuuint64_t)a.w * 4;
+    const cuuint64_t n_ctiles = (a.wc + 7) / 8;
+    cuuint64_t dims[5], strides[4];
+    cuuint32_t box[5] = {8, 0, 0, 1, 1}, es[5] = {1, 1, 1, 1, 1};
+    dims[0] = a.in_tiled ? 8 : a.wc;
+    const cuuint64_t in_blocks = a.in_tiled ? n_ctiles * a.in_blocks : (a.in_stride ? a.n_cosets : 1);
+    if (!perm) {
+        dims[1] = 1ull << q2; dims[2] = 1ull << q1; dims[3] = 1ull << lowbits; dims[4] = in_blocks << a.l0;
+        strides[0] = pitch << lowbits; strides[1] = pitch << (lowbits + q2); strides[2] = pitch; strides[3] = pitch << (a.log_n - a.l0);
+        box[1] = (1u << q2) + 1; box[2] = 1u << q1;
+    } else {
+        dims[1] = 1ull << q1; dims[2] = 1ull << q2; dims[3] = 1; dims[4] = in_blocks << (a.log_n - r);
+        strides[0] = pitch; strides[1] = pitch << q1; strides[2] = pitch; strides[3] = pitch << r;
+        box[1] = (1u << q1) + 1; box[2] = 1u << q2;
+    }
+    const CUresult rc = enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT32, 5, const_cast<u32 *>(a.in), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    P3_CHECK(rc == CUDA_SUCCESS, P3GPU_ECUDA, "cuTensorMapEncodeTiled failed (%d)", (int)rc);
+    return P3GPU_OK;
+}
+
+static bool pipe_eligible(const PassArgs &a) {
+    static const int enabled = env_int("P3GPU_NTT_PIPE", 1);
+    if (!enabled) return false;
+    const int r = a.l1 - a.l0;
+    if (r < 6 || r > 10) return false;
+    if (a.in_tiled || a.out_tiled) return true;                                 // set up by lde_tiled_impl, which checked
+    if (a.w % 4 != 0 || a.w < 8) return false;                                  // TMA: 16-byte global strides
+    if (reinterpret_cast<uintptr_t>(a.in) % 16 != 0) return false;
+    if ((((size_t)a.w * 4) << a.log_n) >= (1ull << 40)) return false;           // TMA stride limit
+    if (a.in_stride != 0 && a.in_stride != ((size_t)a.w << a.log_n)) return false;
+    if (a.in_bitrev && (a.l0 != 0 || (a.in_stride != 0 && a.n_cosets > 1))) return false;
+    return true;
+}
+
+template <int F, int R_LOG, bool PERM>
+static int32_t launch_pipe_r(p3gpu_ctx *ctx, PassArgs a) {
+    constexpr int NSTAGE = 6, NGROUP = 4, GTHREADS = 128;
+    constexpr int Q2 = (R_LOG + 1) / 2, Q1 = R_LOG - Q2;
+    constexpr size_t GS = PERM ? (1u << Q1) : (1u << Q2), NG = PERM ? (1u << Q2) : (1u << Q1);
+    constexpr size_t box_bytes = NG * (GS + 1) * 8 * 4;
+    constexpr size_t smem = NSTAGE * box_bytes + 2 * ((size_t)1 << R_LOG) * sizeof(uint2) + (2 * NSTAGE + 4) * 8;
+    static_assert(smem <= 227 * 1024, "pipelined NTT kernel: shared memory budget");
+    CUtensorMap tm;
+    if (a.wc == 0) a.wc = a.w;
+    if (a.in_blocks == 0) a.in_blocks = 1;
+    P3_TRY(make_pass_tensor_map(a, PERM, &tm));
+    a.n_ctiles = (a.wc + 7) / 8;
+    const size_t units = ((size_t)1 << (a.log_n - R_LOG)) * a.n_cosets;
+    // few units (small transforms): split a unit's column tiles over several CTAs so that every SM has work
+    size_t csplit = units >= 2 * (size_t)ctx->sm_count ? 1 : std::min<size_t>(a.n_ctiles, (2 * (size_t)ctx->sm_count + units - 1) / units);
+    a.tpi = (u32)((a.n_ctiles + csplit - 1) / csplit);
+    csplit = (a.n_ctiles + a.tpi - 1) / a.tpi;
+    a.csplit = (u32)csplit;
+    const size_t items = units * csplit;
+    P3_CHECK(items < (1ull << 31), P3GPU_EINVAL, "ntt: too many tiles");
+    a.n_items = (u32)items;
+    auto kern = ntt_pass_pipe_kernel<F, R_LOG, PERM, NSTAGE, NGROUP, GTHREADS>;
+    static bool attr_set[64] = {false};
+    if (!attr_set[ctx->device & 63]) {
+        P3_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set[ctx->device & 63] = true;
+    }
+    const size_t grid = std::min(items, (size_t)ctx->sm_count);
+    kern<<<(unsigned)grid, NGROUP * GTHREADS + 32, smem, ctx->stream>>>(tm, a);
+    ctx->launches++;
+    P3_CUDA(cudaGetLastError());
+    return P3GPU_OK;
+}
+template <int F, int R_LOG>
+static int32_t launch_pipe_p(p3gpu_ctx *ctx, const PassArgs &a) {
+    return a.in_bitrev ? launch_pipe_r<F, R_LOG, true>(ctx, a) : launch_pipe_r<F, R_LOG, false>(ctx, a);
+}
+template <int F>
+static int32_t launch_pipe(p3gpu_ctx *ctx, const PassArgs &a) {
+    switch (a.l1 - a.l0) {
+        case 6: return launch_pipe_p<F, 6>(ctx, a);
+        case 7: return launch_pipe_p<F, 7>(ctx, a);
+        case 8: return launch_pipe_p<F, 8>(ctx, a);
+        case 9: return launch_pipe_p<F, 9>(ctx, a);
+        default: return launch_pipe_p<F, 10>(ctx, a);
+    }
+}
+
 // Column tile width of the fast kernel: all tiles of a launch share one width (a ragged last tile is allowed).
 // Prefer exact divisors that keep 16-byte alignment (16, 20, 24 columns = 64/80/96-byte row segments).
 static u32 choose_tile_width(u32 w) {
@@ -568,6 +925,14 @@ template <int F>
 static int32_t launch_pass(p3gpu_ctx *ctx, PassArgs a, unsigned n_cosets, int main_log_ct) {
     a.n_cosets = n_cosets;
     const int r = a.l1 - a.l0;
+#ifdef P3GPU_NTT_PROFILE
+    {   // each launch gets its own 1 MiB window of the timeline buffer
+        static int launch_no = 0;
+        const char *pb = getenv("P3GPU_NTT_PROFBUF");
+        a.prof = pb ? reinterpret_cast<unsigned long long *>(strtoull(pb, nullptr, 0)) + (size_t)(launch_no++ % 8) * (1u << 17) : nullptr;
+    }
+#endif
+    if (!env_int("P3GPU_NTT_GENERIC", 0) && pipe_eligible(a)) return launch_pipe<F>(ctx, a);
     if (r >= 6 && r <= 10 && !env_int("P3GPU_NTT_GENERIC", 0)) {
         const u32 ct = choose_tile_width(a.w);
         // 16-byte cp.async / TMA bulk stores need every row segment of every tile 16-byte aligned on both sides
@@ -687,6 +1052,77 @@ static int32_t dft_batch_impl(p3gpu_ctx *ctx, int kind, const u32 *d_in, u32 *d_
     return P3GPU_OK;
 }
 
+// coset_lde_batch (bit-reversed output rows) on the pipelined kernel with COLUMN-TILE-MAJOR intermediates.
+// Between passes the data lives as one 8-column matrix (32-byte rows) per column tile and coset ("tiled" layout): every
+// 32-byte row segment a pass touches is then one aligned DRAM sector, and the contiguous passes stream whole 32 KB tiles.
+// In the caller's dense layout a 400-byte pitch (w = 100) puts every odd row's segments across two sectors, which cost the
+// strided passes ~30 % (profiles/README.md).  Only the first pass (TMA reads) and the last pass (contiguous rows, neighbouring
+// column tiles written back to back by the same CTA) touch the dense layout.  Wide matrices go through in column chunks so
+// that the two intermediates stay small (and L2-friendly) whatever the width.
+//   inverse:  d_in (dense) --pass--> A (tiled) --passes in place--> A = coefficients, network order, lazy range
+//   forward:  A --PERM pass, per coset--> B (tiled, 2^added_bits blocks per tile) --passes in place--> last pass --> d_out (dense)
+template <int F>
+static int32_t lde_tiled_impl(p3gpu_ctx *ctx, const u32 *d_in, size_t h, size_t w, unsigned added_bits, u32 shift, u32 *d_out, bool *done) {
+    *done = false;
+    const int log_n = (int)log2_floor(h);
+    const int max_r = std::min(10, std::max(6, env_int("P3GPU_NTT_MAXR", 10)));
+    const NetworkPlan plan = plan_passes(log_n, max_r);
+    static const int enabled = env_int("P3GPU_NTT_PIPE", 1) && env_int("P3GPU_NTT_TILED", 1);
+    if (!enabled || plan.n_passes < 2 || plan.n_passes > 6) return P3GPU_OK;
+    for (int k = 0; k < plan.n_passes; k++) {
+        const int r = plan.bounds[k + 1] - plan.bounds[k];
+        if (r < 6 || r > 10) return P3GPU_OK;
+    }
+    if (w % 4 != 0 || w < 8 || (reinterpret_cast<uintptr_t>(d_in) | reinterpret_cast<uintptr_t>(d_out)) % 16 != 0) return P3GPU_OK;
+    if (((w * 4) << log_n) >= (1ull << 40) || tensor_map_encoder() == nullptr) return P3GPU_OK;
+    const size_t n_cosets = (size_t)1 << added_bits;
+    // column chunk: keep B (n_cosets * h * chunk * 4 bytes) around 1 GiB, at least 64 columns
+    size_t chunk = ((size_t)1 << 28) / (n_cosets * h);
+    chunk = std::max<size_t>(64, chunk & ~(size_t)7);
+    if (const int forced = env_int("P3GPU_NTT_CHUNK", 0)) chunk = (size_t)std::max(8, forced & ~7);   // tests: exercise the chunk loop
+    const size_t w8 = (w + 7) & ~(size_t)7;
+    chunk = std::min(chunk, w8);
+
+    const uint2 *tw_inv = nullptr, *tw = nullptr;
+    P3_TRY(get_twiddles<F>(ctx, log_n, 0, Fp<F>::ONE, 1, &tw_inv));
+    P3_TRY(get_twiddles<F>(ctx, log_n, (int)added_bits, shift, 0, &tw));
+    void *A = nullptr, *B = nullptr;
+    P3_TRY(ctx_scratch(ctx, h * chunk * 4, &A));
+    P3_TRY(ctx_scratch2(ctx, n_cosets * h * chunk * 4, &B));
+
+    // the inverse network runs its passes in reverse plan order so that its LAST pass and the forward network's FIRST pass
+    // cover the same number of layers (same tile shape on the coefficient buffer)
+    for (size_t col0 = 0; col0 < w; col0 += chunk) {
+        const size_t wc = std::min(chunk, w - col0);
+        for (int k = 0; k < plan.n_passes; k++) {          // inverse
+            PassArgs a;
+            memset(&a, 0, sizeof a);
+            const int kk = plan.n_passes - 1 - k;            // reversed plan: bounds mirrored
+            a.l0 = log_n - plan.bounds[kk + 1]; a.l1 = log_n - plan.bounds[kk];
+            a.w = (u32)w; a.wc = (u32)wc; a.log_n = log_n; a.n_cosets = 1; a.in_blocks = 1;
+            a.tw = tw_inv; a.tw_stride = 0;
+            if (k == 0) { a.in = d_in + col0; a.in_tiled = 0; a.has_scale = 1; a.scale = inv_height_scale<F>(h); }
+            else { a.in = (const u32 *)A; a.in_tiled = 1; }
+            a.out = (u32 *)A; a.out_tiled = 1;
+            P3_TRY(launch_pipe<F>(ctx, a));
+        }
+        for (int k = 0; k < plan.n_passes; k++) {          // forward, all cosets per launch
+            PassArgs a;
+            memset(&a, 0, sizeof a);
+            a.l0 = plan.bounds[k]; a.l1 = plan.bounds[k + 1];
+            a.w = (u32)w; a.wc = (u32)wc; a.log_n = log_n; a.n_cosets = (u32)n_cosets;
+            a.tw = tw; a.tw_stride = h;
+            if (k == 0) { a.in = (const u32 *)A; a.in_tiled = 1; a.in_blocks = 1; a.in_bitrev = 1; }
+            else { a.in = (const u32 *)B; a.in_tiled = 1; a.in_blocks = (u32)n_cosets; }
+            if (k == plan.n_passes - 1) { a.out = d_out + col0; a.out_tiled = 0; a.out_stride = h * w; a.final_reduce = 1; }
+            else { a.out = (u32 *)B; a.out_tiled = 1; }
+            P3_TRY(launch_pipe<F>(ctx, a));
+        }
+    }
+    *done = true;
+    return P3GPU_OK;
+}
+
 template <int F>
 static int32_t coset_lde_impl(p3gpu_ctx *ctx, const u32 *d_in, size_t h, size_t w, unsigned added_bits, u32 shift, u32 *d_out,
                               int bitrev_rows) {
@@ -698,6 +1134,11 @@ static int32_t coset_lde_impl(p3gpu_ctx *ctx, const u32 *d_in, size_t h, size_t 
         ctx->launches++;
         P3_CUDA(cudaGetLastError());
         return P3GPU_OK;
+    }
+    if (bitrev_rows) {
+        bool done = false;
+        P3_TRY(lde_tiled_impl<F>(ctx, d_in, h, w, added_bits, shift, d_out, &done));
+        if (done) return P3GPU_OK;
     }
     // 1) inverse network: evaluations on H (natural) -> coefficients in network (bit-reversed) order, scaled by 1/h
     const uint2 *tw_inv = nullptr;

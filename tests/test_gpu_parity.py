@@ -83,7 +83,8 @@ def test_small_dft_vs_naive_definition(gpu, f):
 
 
 @pytest.mark.parametrize("f", FIELDS, ids=lambda f: f.name)
-@pytest.mark.parametrize("log_h,w,added_bits", [(0, 2, 1), (1, 3, 2), (4, 5, 0), (4, 5, 1), (6, 9, 3), (10, 100, 1), (12, 37, 1), (13, 8, 2), (14, 4, 1), (10, 33, 1), (9, 45, 2)])
+@pytest.mark.parametrize("log_h,w,added_bits", [(0, 2, 1), (1, 3, 2), (4, 5, 0), (4, 5, 1), (6, 9, 3), (10, 100, 1), (12, 37, 1), (13, 8, 2), (14, 4, 1), (10, 33, 1), (9, 45, 2),
+                                                  (12, 100, 1), (16, 40, 2), (14, 128, 1), (13, 12, 1), (15, 8, 0)])
 def test_coset_lde_matches_oracle(gpu, f, log_h, w, added_bits):
     # traits.rs:227-259 + radix_2_dit_parallel.rs:181-246: values AND memory layout (bit-reversed rows)
     dft = Radix2DitParallel(f, gpu)
@@ -107,6 +108,18 @@ def test_large_heights_three_pass_plans(gpu, f, log_h, w):
     if log_h <= 22:
         got = dft.coset_lde_batch(dev(m), 1, f.generator).bit_reverse_rows()
         assert np.array_equal(host(got), O.coset_lde_batch(f.id, m, 1, f.generator, bitrev_out=True))
+
+
+@pytest.mark.parametrize("f,log_h,w,added_bits,chunk", [(KoalaBear, 13, 52, 1, 16), (BabyBear, 12, 100, 2, 24), (KoalaBear, 21, 8, 1, 0), (BabyBear, 19, 12, 1, 8)])
+def test_coset_lde_tiled_intermediates(gpu, f, log_h, w, added_bits, chunk, monkeypatch):
+    # the pipelined LDE keeps its intermediates column-tile-major and walks wide matrices in column chunks (csrc/ntt.cu
+    # lde_tiled_impl); P3GPU_NTT_CHUNK forces small chunks so that the chunk loop and ragged last tiles are exercised
+    if chunk:
+        monkeypatch.setenv("P3GPU_NTT_CHUNK", str(chunk))
+    dft = Radix2DitParallel(f, gpu)
+    m = O.random_matrix(f.id, 1 << log_h, w, seed=3 * log_h + w)
+    got = dft.coset_lde_batch(dev(m), added_bits, f.generator).bit_reverse_rows()
+    assert np.array_equal(host(got), O.coset_lde_batch(f.id, m, added_bits, f.generator, bitrev_out=True))
 
 
 def test_dft_shape_errors(gpu):
