@@ -290,10 +290,10 @@ def main():
     tp = ROOT / "profiles" / "ncu_traffic.json"
     if tp.exists():
         traffic = json.loads(tp.read_text()).get("lde_step_dram_bytes")
-    line["roofline"] = {"bound": "hbm", "kernel": "ntt_pass_fast_kernel (all launches of an LDE step)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    line["roofline"] = {"bound": "hbm", "kernel": "ntt_pass_pipe_kernel (all launches of an LDE step)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                         "algorithmic_bytes_per_step": ALG_BYTES, "launches_per_step": launches / args.steps,
-                        "note": "integer-pipe bound, not HBM bound: 3.146e9 butterflies x (IMAD.HI + 2 IMAD + 4 ALU); register-only butterfly loop peaks at 12.85/clk/SM = 0.86 ms floor (DESIGN.md 4.1)"}
+                        "note": "integer-pipe bound, not HBM bound: 3.146e9 butterflies x (IMAD.HI + 2 IMAD + 4 ALU) = 73 % of the issued instructions; register-only butterfly loop peaks at 12.85/clk/SM = 0.86 ms floor (DESIGN.md 4.1)"}
 
     # ---- secondary workloads (single GPU only)
     if world == 1 and not args.no_others:

@@ -22,6 +22,7 @@
 // evaluations in network order — which is exactly the bit-reversed row order the reference leaves in memory
 // (radix_2_dit_parallel.rs:245, fri/src/two_adic_pcs.rs:313-318).  No standalone bit-reversal or scaling pass exists.
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 
@@ -467,8 +468,8 @@ __global__ void __launch_bounds__(NGROUP * GTHREADS + 32, 1) ntt_pass_pipe_kerne
     auto twempty_bar = [&](u32 b) { return bar0 + 8u * (2 * NSTAGE + 2 + b); };
 
     if (threadIdx.x == 0) {
-        for (u32 s = 0; s < NSTAGE; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), GTHREADS); }
-        for (u32 b = 0; b < 2; b++) { mbar_init(twfull_bar(b), 1); mbar_init(twempty_bar(b), a.tpi * GTHREADS); }
+        for (u32 s = 0; s < NSTAGE; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), NGROUP * GTHREADS); }
+        for (u32 b = 0; b < 2; b++) { mbar_init(twfull_bar(b), 1); mbar_init(twempty_bar(b), a.tpi * NGROUP * GTHREADS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -494,7 +495,7 @@ __global__ void __launch_bounds__(NGROUP * GTHREADS + 32, 1) ntt_pass_pipe_kerne
             decode(it, coset, L, T, ct0, ct1);
             const u32 b = ui & 1u, ph = (ui >> 1) & 1u;
             mbar_wait(twempty_bar(b), ph ^ 1u);   // every tile of unit ui-2 is done with this twiddle buffer
-            if (ct1 - ct0 < a.tpi) mbar_arrive_n(twempty_bar(b), (a.tpi - (ct1 - ct0)) * GTHREADS);   // short last chunk
+            if (ct1 - ct0 < a.tpi) mbar_arrive_n(twempty_bar(b), (a.tpi - (ct1 - ct0)) * NGROUP * GTHREADS);   // short last chunk
             {
                 const uint2 *tw = a.tw + (size_t)coset * a.tw_stride;
                 uint2 *tws = tws0 + b * R;
@@ -545,13 +546,22 @@ __global__ void __launch_bounds__(NGROUP * GTHREADS + 32, 1) ntt_pass_pipe_kerne
         const u32 ibase = (a.l0 == 0 ? 0u : (T << (a.log_n - a.l0))) | L;
         bool tw_ready = false;
         for (u32 ct = ct0; ct < ct1; ct++, q++) {
-            if (q % NGROUP != gid) continue;
             const u32 s = q % NSTAGE, k = q / NSTAGE;
             const u32 col = ct * CT, cw = min(CT, a.wc - col);
             u32 *data = stages + (size_t)s * STAGE_WORDS;
             P3_GSTAMP(1);
+            // EVERY group waits for EVERY tile and twiddle buffer in sequence order, also those it does not process, and only then
+            // lets the ring advance (empty[s] / twempty[b] count all consumer threads).  A parity wait can only tell the current
+            // mbarrier phase from the one before it; a group that skipped a stage's previous use could otherwise run ahead of a
+            // load that is still in flight and take the older phase for the one it wants (seen with 128-row tiles, which are
+            // processed faster than HBM latency varies: corrupted arrival counts, i.e. hangs and mbarrier traps).
             mbar_wait(full_bar(s), k & 1u);
             if (!tw_ready) { mbar_wait(twfull_bar(b), ph); tw_ready = true; }
+            if (q % NGROUP != gid) {
+                mbar_arrive(empty_bar(s));
+                mbar_arrive(twempty_bar(b));
+                continue;
+            }
             P3_GSTAMP(2);
             const u32 dg = GTHREADS / cw, dc = GTHREADS - dg * cw;
             // ---- step 1 (in place): E1 values per item, Q1 layers
@@ -842,12 +852,11 @@ static int32_t make_pass_tensor_map(const PassArgs &a, bool perm, CUtensorMap *t
 }
 
 static bool pipe_eligible(const PassArgs &a) {
-    static const int enabled = env_int("P3GPU_NTT_PIPE", 1);
-    if (!enabled) return false;
+    if (!env_int("P3GPU_NTT_PIPE", 1)) return false;   // read per call: the tests switch between the two kernel families
     const int r = a.l1 - a.l0;
     if (r < 6 || r > 10) return false;
     if (a.in_tiled || a.out_tiled) return true;                                 // set up by lde_tiled_impl, which checked
-    if (a.w % 4 != 0 || a.w < 8) return false;                                  // TMA: 16-byte global strides
+    if (a.w % 4 != 0 || a.w < 8 || a.w > 8192) return false;                    // TMA: 16-byte global strides; mbarrier count per unit
     if (reinterpret_cast<uintptr_t>(a.in) % 16 != 0) return false;
     if ((((size_t)a.w * 4) << a.log_n) >= (1ull << 40)) return false;           // TMA stride limit
     if (a.in_stride != 0 && a.in_stride != ((size_t)a.w << a.log_n)) return false;
@@ -876,6 +885,7 @@ static int32_t launch_pipe_r(p3gpu_ctx *ctx, PassArgs a) {
     a.csplit = (u32)csplit;
     const size_t items = units * csplit;
     P3_CHECK(items < (1ull << 31), P3GPU_EINVAL, "ntt: too many tiles");
+    P3_CHECK((size_t)a.tpi * NGROUP * GTHREADS < (1u << 20), P3GPU_EINVAL, "ntt: too many column tiles per unit for the mbarrier count");
     a.n_items = (u32)items;
     auto kern = ntt_pass_pipe_kernel<F, R_LOG, PERM, NSTAGE, NGROUP, GTHREADS>;
     static bool attr_set[64] = {false};
@@ -1067,7 +1077,7 @@ static int32_t lde_tiled_impl(p3gpu_ctx *ctx, const u32 *d_in, size_t h, size_t 
     const int log_n = (int)log2_floor(h);
     const int max_r = std::min(10, std::max(6, env_int("P3GPU_NTT_MAXR", 10)));
     const NetworkPlan plan = plan_passes(log_n, max_r);
-    static const int enabled = env_int("P3GPU_NTT_PIPE", 1) && env_int("P3GPU_NTT_TILED", 1);
+    const bool enabled = env_int("P3GPU_NTT_PIPE", 1) && env_int("P3GPU_NTT_TILED", 1);
     if (!enabled || plan.n_passes < 2 || plan.n_passes > 6) return P3GPU_OK;
     for (int k = 0; k < plan.n_passes; k++) {
         const int r = plan.bounds[k + 1] - plan.bounds[k];
@@ -1081,7 +1091,7 @@ static int32_t lde_tiled_impl(p3gpu_ctx *ctx, const u32 *d_in, size_t h, size_t 
     chunk = std::max<size_t>(64, chunk & ~(size_t)7);
     if (const int forced = env_int("P3GPU_NTT_CHUNK", 0)) chunk = (size_t)std::max(8, forced & ~7);   // tests: exercise the chunk loop
     const size_t w8 = (w + 7) & ~(size_t)7;
-    chunk = std::min(chunk, w8);
+    chunk = std::min(std::min(chunk, w8), (size_t)8192);
 
     const uint2 *tw_inv = nullptr, *tw = nullptr;
     P3_TRY(get_twiddles<F>(ctx, log_n, 0, Fp<F>::ONE, 1, &tw_inv));

@@ -122,6 +122,21 @@ def test_coset_lde_tiled_intermediates(gpu, f, log_h, w, added_bits, chunk, monk
     assert np.array_equal(host(got), O.coset_lde_batch(f.id, m, added_bits, f.generator, bitrev_out=True))
 
 
+@pytest.mark.parametrize("f,log_h,w", [(BabyBear, 21, 200), (KoalaBear, 22, 72)])
+def test_lde_many_small_tiles_pipelined_vs_cp_async_kernels(gpu, f, log_h, w, monkeypatch):
+    # three-pass plans have 128/256-row tiles that are processed faster than HBM latency varies: the regime in which a consumer
+    # group of the pipelined kernel can run ahead of an in-flight load (mbarrier phase handling, csrc/ntt.cu).  Too large for the
+    # CPU oracle in a unit test, so the two independent kernel families (TMA pipeline vs cp.async tiles) must agree bit for bit.
+    x = torch.randint(0, f.P, (1 << log_h, w), device="cuda", dtype=torch.int32, generator=torch.Generator(device="cuda").manual_seed(log_h))
+    monkeypatch.setenv("P3GPU_NTT_PIPE", "0")
+    want = gpu.coset_lde_batch(f.id, x, 1, f.generator)
+    monkeypatch.setenv("P3GPU_NTT_PIPE", "1")
+    for _ in range(3):
+        got = gpu.coset_lde_batch(f.id, x, 1, f.generator)
+        assert torch.equal(got, want)
+        del got
+
+
 def test_dft_shape_errors(gpu):
     # the reference panics in log2_strict_usize on non power-of-two heights; the C ABI returns P3GPU_EINVAL
     with pytest.raises(P.P3GpuError, match="power of two"):
