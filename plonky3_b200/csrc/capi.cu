@@ -96,16 +96,19 @@ void p3gpu_ctx_destroy(p3gpu_ctx *ctx) {
 
 int32_t p3gpu_ctx_set_stream(p3gpu_ctx *ctx, void *cuda_stream) {
     P3_CHECK(ctx, P3GPU_EINVAL, "null context");
+    P3_CUDA(cudaSetDevice(ctx->device));   // CUDA's current device is per host thread: callers may come from any thread
     ctx->stream = (cudaStream_t)cuda_stream;  // NULL is the legacy default stream (what torch uses by default)
     return P3GPU_OK;
 }
 int32_t p3gpu_ctx_use_own_stream(p3gpu_ctx *ctx) {
     P3_CHECK(ctx, P3GPU_EINVAL, "null context");
+    P3_CUDA(cudaSetDevice(ctx->device));   // CUDA's current device is per host thread: callers may come from any thread
     ctx->stream = ctx->own_stream;
     return P3GPU_OK;
 }
 int32_t p3gpu_ctx_sync(p3gpu_ctx *ctx) {
     P3_CHECK(ctx, P3GPU_EINVAL, "null context");
+    P3_CUDA(cudaSetDevice(ctx->device));   // CUDA's current device is per host thread: callers may come from any thread
     P3_CUDA(cudaStreamSynchronize(ctx->stream));
     return P3GPU_OK;
 }
@@ -120,16 +123,19 @@ int32_t p3gpu_malloc(p3gpu_ctx *ctx, size_t bytes, void **dptr) {
 }
 int32_t p3gpu_free(p3gpu_ctx *ctx, void *dptr) {
     P3_CHECK(ctx, P3GPU_EINVAL, "null context");
+    P3_CUDA(cudaSetDevice(ctx->device));   // CUDA's current device is per host thread: callers may come from any thread
     if (dptr) { P3_CUDA(cudaStreamSynchronize(ctx->stream)); P3_CUDA(cudaFree(dptr)); }
     return P3GPU_OK;
 }
 int32_t p3gpu_memcpy_h2d(p3gpu_ctx *ctx, void *dst, const void *src, size_t bytes) {
     P3_CHECK(ctx, P3GPU_EINVAL, "null context");
+    P3_CUDA(cudaSetDevice(ctx->device));   // CUDA's current device is per host thread: callers may come from any thread
     P3_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
     return P3GPU_OK;
 }
 int32_t p3gpu_memcpy_d2h(p3gpu_ctx *ctx, void *dst, const void *src, size_t bytes) {
     P3_CHECK(ctx, P3GPU_EINVAL, "null context");
+    P3_CUDA(cudaSetDevice(ctx->device));   // CUDA's current device is per host thread: callers may come from any thread
     P3_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     P3_CUDA(cudaStreamSynchronize(ctx->stream));
     return P3GPU_OK;
@@ -147,10 +153,12 @@ int32_t p3gpu_host_unregister(void *ptr) {
 int32_t p3gpu_dft_batch_dev(p3gpu_ctx *ctx, int field, int kind, const uint32_t *d_in, uint32_t *d_out, size_t h, size_t w,
                             uint32_t shift) {
     P3_CHECK(ctx && d_in && d_out, P3GPU_EINVAL, "null argument");
+    P3_CUDA(cudaSetDevice(ctx->device));   // CUDA's current device is per host thread: callers may come from any thread
     return ntt_dft_batch(ctx, field, kind, d_in, d_out, h, w, shift);
 }
 int32_t p3gpu_dft_batch(p3gpu_ctx *ctx, int field, int kind, uint32_t *h_inout, size_t h, size_t w, uint32_t shift) {
     P3_CHECK(ctx && h_inout, P3GPU_EINVAL, "null argument");
+    P3_CUDA(cudaSetDevice(ctx->device));   // CUDA's current device is per host thread: callers may come from any thread
     void *buf = nullptr;
     P3_TRY(ctx_pool(ctx, 0, h * w * 4, &buf));
     P3_CUDA(cudaMemcpyAsync(buf, h_inout, h * w * 4, cudaMemcpyHostToDevice, ctx->stream));
@@ -162,11 +170,13 @@ int32_t p3gpu_dft_batch(p3gpu_ctx *ctx, int field, int kind, uint32_t *h_inout, 
 int32_t p3gpu_coset_lde_batch_dev(p3gpu_ctx *ctx, int field, const uint32_t *d_in, size_t h, size_t w, unsigned added_bits,
                                   uint32_t shift, uint32_t *d_out, int bitrev_rows) {
     P3_CHECK(ctx && d_in && d_out, P3GPU_EINVAL, "null argument");
+    P3_CUDA(cudaSetDevice(ctx->device));   // CUDA's current device is per host thread: callers may come from any thread
     return ntt_coset_lde(ctx, field, d_in, h, w, added_bits, shift, d_out, bitrev_rows);
 }
 int32_t p3gpu_coset_lde_batch(p3gpu_ctx *ctx, int field, const uint32_t *h_in, size_t h, size_t w, unsigned added_bits,
                               uint32_t shift, uint32_t *h_out, int bitrev_rows) {
     P3_CHECK(ctx && h_in && h_out, P3GPU_EINVAL, "null argument");
+    P3_CUDA(cudaSetDevice(ctx->device));   // CUDA's current device is per host thread: callers may come from any thread
     P3_CHECK(added_bits <= 8, P3GPU_EINVAL, "added_bits %u too large", added_bits);
     void *in = nullptr, *out = nullptr;
     const size_t nin = h * w * 4, nout = nin << added_bits;
@@ -183,6 +193,7 @@ int32_t p3gpu_coset_lde_batch(p3gpu_ctx *ctx, int field, const uint32_t *h_in, s
 int32_t p3gpu_poseidon2_set_constants(p3gpu_ctx *ctx, int field, int width, const uint32_t *rc_initial, const uint32_t *rc_terminal,
                                       const uint32_t *rc_internal, int rounds_p) {
     P3_CHECK(ctx && rc_initial && rc_terminal && rc_internal, P3GPU_EINVAL, "null argument");
+    P3_CUDA(cudaSetDevice(ctx->device));   // CUDA's current device is per host thread: callers may come from any thread
     P3_CHECK(field == BABY_BEAR || field == KOALA_BEAR, P3GPU_EUNSUPPORTED, "unknown field %d", field);
     P3_CHECK(width == 16 || width == 24, P3GPU_EUNSUPPORTED, "Poseidon2 width %d unsupported (16 or 24)", width);
     P3_CHECK(rounds_p >= 1 && rounds_p <= 32, P3GPU_EINVAL, "rounds_p %d out of range", rounds_p);
@@ -202,10 +213,12 @@ int32_t p3gpu_poseidon2_set_constants(p3gpu_ctx *ctx, int field, int width, cons
 }
 int32_t p3gpu_poseidon2_permute_dev(p3gpu_ctx *ctx, int field, int width, uint32_t *d_states, size_t n) {
     P3_CHECK(ctx && d_states, P3GPU_EINVAL, "null argument");
+    P3_CUDA(cudaSetDevice(ctx->device));   // CUDA's current device is per host thread: callers may come from any thread
     return hash_poseidon2_permute(ctx, field, width, d_states, n);
 }
 int32_t p3gpu_keccak_f_dev(p3gpu_ctx *ctx, uint64_t *d_states, size_t n) {
     P3_CHECK(ctx && d_states, P3GPU_EINVAL, "null argument");
+    P3_CUDA(cudaSetDevice(ctx->device));   // CUDA's current device is per host thread: callers may come from any thread
     return hash_keccak_f(ctx, d_states, n);
 }
 
@@ -219,12 +232,14 @@ int32_t p3gpu_merkle_commit_dev(p3gpu_ctx *ctx, int field, int hash, size_t n_ma
                                 const size_t *heights, const size_t *widths, uint32_t *d_layers, size_t *layer_lens,
                                 size_t *n_layers) {
     P3_CHECK(ctx && d_mats && heights && widths && d_layers && layer_lens && n_layers, P3GPU_EINVAL, "null argument");
+    P3_CUDA(cudaSetDevice(ctx->device));   // CUDA's current device is per host thread: callers may come from any thread
     return hash_merkle_commit(ctx, field, hash, n_mats, d_mats, heights, widths, d_layers, layer_lens, n_layers);
 }
 int32_t p3gpu_merkle_commit(p3gpu_ctx *ctx, int field, int hash, size_t n_mats, const uint32_t *const *h_mats,
                             const size_t *heights, const size_t *widths, uint32_t *h_layers, size_t *layer_lens,
                             size_t *n_layers) {
     P3_CHECK(ctx && h_mats && heights && widths && h_layers && layer_lens && n_layers, P3GPU_EINVAL, "null argument");
+    P3_CUDA(cudaSetDevice(ctx->device));   // CUDA's current device is per host thread: callers may come from any thread
     P3_CHECK(n_mats >= 1 && n_mats <= 1024, P3GPU_EINVAL, "No matrices given?");
     std::vector<DevBuf> bufs(n_mats);
     std::vector<const u32 *> ptrs(n_mats);
@@ -248,6 +263,7 @@ int32_t p3gpu_merkle_commit(p3gpu_ctx *ctx, int field, int hash, size_t n_mats, 
 int32_t p3gpu_merkle_from_digests_dev(p3gpu_ctx *ctx, int field, int hash, const uint32_t *d_digests, size_t n, uint32_t *d_layers,
                                       size_t *layer_lens, size_t *n_layers) {
     P3_CHECK(ctx && d_digests && d_layers && layer_lens && n_layers, P3GPU_EINVAL, "null argument");
+    P3_CUDA(cudaSetDevice(ctx->device));   // CUDA's current device is per host thread: callers may come from any thread
     return hash_merkle_from_digests(ctx, field, hash, d_digests, n, d_layers, layer_lens, n_layers);
 }
 
@@ -255,11 +271,13 @@ int32_t p3gpu_merkle_from_digests_dev(p3gpu_ctx *ctx, int field, int hash, const
 int32_t p3gpu_fri_fold_dev(p3gpu_ctx *ctx, int field, const uint32_t *d_in, size_t rows, unsigned log_arity, const uint32_t beta[4],
                            uint32_t *d_out) {
     P3_CHECK(ctx && d_in && d_out && beta, P3GPU_EINVAL, "null argument");
+    P3_CUDA(cudaSetDevice(ctx->device));   // CUDA's current device is per host thread: callers may come from any thread
     return fri_fold(ctx, field, d_in, rows, log_arity, beta, d_out);
 }
 int32_t p3gpu_fri_fold(p3gpu_ctx *ctx, int field, const uint32_t *h_in, size_t rows, unsigned log_arity, const uint32_t beta[4],
                        uint32_t *h_out) {
     P3_CHECK(ctx && h_in && h_out && beta, P3GPU_EINVAL, "null argument");
+    P3_CUDA(cudaSetDevice(ctx->device));   // CUDA's current device is per host thread: callers may come from any thread
     P3_CHECK(log_arity >= 1 && log_arity <= 4, P3GPU_EINVAL, "log_arity %u out of range 1..4", log_arity);
     void *in = nullptr, *out = nullptr;
     const size_t nin = (rows << log_arity) * 16;
@@ -274,6 +292,7 @@ int32_t p3gpu_fri_fold(p3gpu_ctx *ctx, int field, const uint32_t *h_in, size_t r
 
 int32_t p3gpu_ef_axpy_dev(p3gpu_ctx *ctx, int field, uint32_t *d_acc, const uint32_t *d_x, size_t n, const uint32_t s[4]) {
     P3_CHECK(ctx && d_acc && d_x && s, P3GPU_EINVAL, "null argument");
+    P3_CUDA(cudaSetDevice(ctx->device));   // CUDA's current device is per host thread: callers may come from any thread
     return fri_ef_axpy(ctx, field, d_acc, d_x, n, s);
 }
 
@@ -288,6 +307,7 @@ int32_t p3gpu_fri_commit_phase_dev(p3gpu_ctx *ctx, int field, int hash, uint32_t
                                    size_t n_betas, uint32_t *h_caps, size_t *cap_lens, unsigned *log_arities, size_t *n_rounds,
                                    uint32_t *h_final) {
     P3_CHECK(ctx && d_vec && betas && h_caps && cap_lens && log_arities && n_rounds && h_final, P3GPU_EINVAL, "null argument");
+    P3_CUDA(cudaSetDevice(ctx->device));   // CUDA's current device is per host thread: callers may come from any thread
     P3_CHECK(is_pow2(len), P3GPU_EINVAL, "commit phase: length %zu is not a power of two", len);
     P3_CHECK(max_log_arity >= 1 && max_log_arity <= 4, P3GPU_EINVAL, "max_log_arity must be in 1..4 to guarantee folding progress");
     const unsigned log_final = log_blowup + log_final_poly_len;
@@ -326,20 +346,24 @@ int32_t p3gpu_fri_commit_phase_dev(p3gpu_ctx *ctx, int field, int hash, uint32_t
 int32_t p3gpu_open_inv_denoms_dev(p3gpu_ctx *ctx, int field, unsigned log_height, const uint32_t z[4], const uint32_t *zinv,
                                   uint32_t *d_inv_denoms, uint32_t *d_adjusted) {
     P3_CHECK(ctx && z && d_inv_denoms, P3GPU_EINVAL, "null argument");
+    P3_CUDA(cudaSetDevice(ctx->device));   // CUDA's current device is per host thread: callers may come from any thread
     return open_inv_denoms(ctx, field, log_height, z, zinv, d_inv_denoms, d_adjusted);
 }
 int32_t p3gpu_columnwise_dot_dev(p3gpu_ctx *ctx, int field, const uint32_t *d_mat, size_t h, size_t w, const uint32_t *d_vec_ef,
                                  const uint32_t *scale, uint32_t *d_out) {
     P3_CHECK(ctx && d_mat && d_vec_ef && d_out, P3GPU_EINVAL, "null argument");
+    P3_CUDA(cudaSetDevice(ctx->device));   // CUDA's current device is per host thread: callers may come from any thread
     return open_columnwise_dot(ctx, field, d_mat, h, w, d_vec_ef, d_out, scale);
 }
 int32_t p3gpu_rowwise_dot_dev(p3gpu_ctx *ctx, int field, const uint32_t *d_mat, size_t h, size_t w, const uint32_t alpha[4], uint32_t *d_out) {
     P3_CHECK(ctx && d_mat && alpha && d_out, P3GPU_EINVAL, "null argument");
+    P3_CUDA(cudaSetDevice(ctx->device));   // CUDA's current device is per host thread: callers may come from any thread
     return open_rowwise_dot(ctx, field, d_mat, h, w, alpha, d_out);
 }
 int32_t p3gpu_open_reduce_dev(p3gpu_ctx *ctx, int field, uint32_t *d_ro, const uint32_t *d_r, const uint32_t *d_inv_denoms, size_t h,
                               const uint32_t coeff[4], const uint32_t yred[4]) {
     P3_CHECK(ctx && d_ro && d_r && d_inv_denoms && coeff && yred, P3GPU_EINVAL, "null argument");
+    P3_CUDA(cudaSetDevice(ctx->device));   // CUDA's current device is per host thread: callers may come from any thread
     return open_reduce(ctx, field, d_ro, d_r, d_inv_denoms, h, coeff, yred);
 }
 
@@ -347,6 +371,7 @@ int32_t p3gpu_open_reduce_dev(p3gpu_ctx *ctx, int field, uint32_t *d_ro, const u
 int32_t p3gpu_pcs_commit_dev(p3gpu_ctx *ctx, int field, int hash, const uint32_t *d_evals, size_t h, size_t w, unsigned log_blowup,
                              uint32_t *d_lde, uint32_t *d_layers, size_t *layer_lens, size_t *n_layers) {
     P3_CHECK(ctx && d_evals && d_lde && d_layers && layer_lens && n_layers, P3GPU_EINVAL, "null argument");
+    P3_CUDA(cudaSetDevice(ctx->device));   // CUDA's current device is per host thread: callers may come from any thread
     P3_CHECK(field == BABY_BEAR || field == KOALA_BEAR, P3GPU_EUNSUPPORTED, "unknown field %d", field);
     // shift = GENERATOR / domain.shift() with domain.shift() = 1 (two_adic_pcs.rs:312)
     const u32 shift = field == BABY_BEAR ? to_monty<BABY_BEAR>(Fp<BABY_BEAR>::GEN) : to_monty<KOALA_BEAR>(Fp<KOALA_BEAR>::GEN);
