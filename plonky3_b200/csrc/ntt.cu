@@ -17,6 +17,10 @@
 //   * butterflies use Shoup multiplication by the precomputed twiddle and lazy [0, 2p) reduction:
 //     3 multiply-pipe + 6 ALU-pipe instructions each (field.cuh: ct_butterfly).
 //
+// Two kernel generations implement a pass: ntt_pass_pipe_kernel (TMA tile loads into an mbarrier stage ring, warp-specialised
+// consumer groups; the production path for 16-byte aligned shapes, with column-tile-major intermediates for the LDE) and
+// ntt_pass_fast_kernel / ntt_pass_kernel (cp.async or plain loads; every other shape).  P3GPU_NTT_PIPE=0 forces the latter.
+//
 // coset_lde_batch = inverse network (root^-1, scale 1/h) producing coefficients in network (bit-reversed) order,
 // then per coset a forward network reading those coefficients through a bit-reversed row map and leaving the
 // evaluations in network order — which is exactly the bit-reversed row order the reference leaves in memory
