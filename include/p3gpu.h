@@ -21,6 +21,10 @@
  *   - "_dev" variants take DEVICE pointers and run asynchronously on the context's stream; the plain variants
  *     take HOST pointers and include the host<->device copies (they synchronise before returning).
  *   - There is no CPU fallback: without a CUDA device p3gpu_ctx_create fails with P3GPU_ECUDA.
+ *   - Threads and devices: a context belongs to one device and serialises its work on one stream; every entry point makes
+ *     that device current for the calling host thread, so calls may come from any thread (the reference's DFT / MMCS
+ *     objects are Clone + Sync).  One context must not be used by two threads at the same time; use one context per
+ *     thread (each has its own stream, scratch buffers and twiddle cache) to keep several calls in flight.
  */
 #ifndef P3GPU_H
 #define P3GPU_H

@@ -1096,6 +1096,7 @@ static int32_t lde_tiled_impl(p3gpu_ctx *ctx, const u32 *d_in, size_t h, size_t 
     if (const int forced = env_int("P3GPU_NTT_CHUNK", 0)) chunk = (size_t)std::max(8, forced & ~7);   // tests: exercise the chunk loop
     const size_t w8 = (w + 7) & ~(size_t)7;
     chunk = std::min(std::min(chunk, w8), (size_t)8192);
+    if (n_cosets * h * chunk * 4 > ((size_t)8 << 30)) return P3GPU_OK;   // huge blow-ups: the 64-column floor would need > 8 GiB of scratch
 
     const uint2 *tw_inv = nullptr, *tw = nullptr;
     P3_TRY(get_twiddles<F>(ctx, log_n, 0, Fp<F>::ONE, 1, &tw_inv));
