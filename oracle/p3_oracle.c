@@ -108,6 +108,24 @@ static unsigned log2_strict(size_t n) {
     if (((size_t)1 << l) != n) { fprintf(stderr, "p3_oracle: %zu is not a power of two\n", n); abort(); }
     return l;
 }
+/* memcpy and geometric tables split over the OpenMP team (large matrices: a serial copy / first touch of ~0.4 GB costs as much
+ * as a butterfly sweep, and the pages should be touched by the threads that use them) */
+static void par_copy(u32 *dst, const u32 *src, size_t n) {
+    #pragma omp parallel for schedule(static)
+    for (size_t blk = 0; blk < (n + 65535) / 65536; blk++) {
+        size_t o = blk * 65536, len = n - o < 65536 ? n - o : 65536;
+        memcpy(dst + o, src + o, len * 4);
+    }
+}
+static void f_powers(const field_t *f, u32 *pw, size_t n, u32 base) {   /* pw[i] = base^i */
+    const size_t B = 4096;
+    #pragma omp parallel for schedule(static)
+    for (size_t blk = 0; blk < (n + B - 1) / B; blk++) {
+        size_t o = blk * B, e = o + B < n ? o + B : n;
+        u32 v = f_pow(f, base, o);
+        for (size_t i = o; i < e; i++) { pw[i] = v; v = f_mul(f, v, base); }
+    }
+}
 void p3o_reverse_matrix_index_bits(u32 *mat, size_t h, size_t w) {
     unsigned lh = log2_strict(h);
     #pragma omp parallel
@@ -165,8 +183,7 @@ static void dft_rows(const field_t *f, u32 *mat, size_t h, size_t w, u32 root) {
     unsigned lh = log2_strict(h);
     p3o_reverse_matrix_index_bits(mat, h, w);
     u32 *tw = (u32 *)malloc((h / 2) * 4);
-    tw[0] = f_one(f);
-    for (size_t i = 1; i < h / 2; i++) tw[i] = f_mul(f, tw[i - 1], root);
+    f_powers(f, tw, h / 2, root);
     unsigned mid = (lh + 1) / 2;
     size_t B = (size_t)1 << mid, nblk = h >> mid;
     #pragma omp parallel for schedule(static)
@@ -202,8 +219,7 @@ void p3o_dft_batch(int fi, u32 *mat, size_t h, size_t w) {
 /* dft/src/util.rs:32-55 — coset_shift_cols: row i *= shift^i */
 static void coset_shift_rows(const field_t *f, u32 *mat, size_t h, size_t w, u32 shift) {
     u32 *pw = (u32 *)malloc(h * 4);
-    pw[0] = f_one(f);
-    for (size_t i = 1; i < h; i++) pw[i] = f_mul(f, pw[i - 1], shift);
+    f_powers(f, pw, h, shift);
     #pragma omp parallel for schedule(static)
     for (size_t i = 0; i < h; i++) for (size_t c = 0; c < w; c++) mat[i * w + c] = f_mul(f, mat[i * w + c], pw[i]);
     free(pw);
@@ -237,14 +253,14 @@ void p3o_coset_lde_batch(int fi, const u32 *in, size_t h, size_t w, unsigned add
     unsigned lh = log2_strict(h);
     size_t nc = (size_t)1 << added_bits;
     u32 *coeffs = (u32 *)malloc(h * w * 4);
-    memcpy(coeffs, in, h * w * 4);
+    par_copy(coeffs, in, h * w);
     p3o_idft_batch(fi, coeffs, h, w);
     u32 g_big = f_two_adic_generator(f, lh + added_bits);
     u32 *tmp = (u32 *)malloc(h * w * 4);
     for (size_t c = 0; c < nc; c++) {
         /* coset c (natural coset index): points shift * g_big^c * H */
         u32 s = f_mul(f, shift, f_pow(f, g_big, c));
-        memcpy(tmp, coeffs, h * w * 4);
+        par_copy(tmp, coeffs, h * w);
         p3o_coset_dft_batch(fi, tmp, h, w, s);
         /* natural LDE index of (coset c, j) is j*nc + c */
         #pragma omp parallel for schedule(static)
