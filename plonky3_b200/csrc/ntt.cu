@@ -443,9 +443,20 @@ __global__ void __launch_bounds__(THREADS, NBUF == 2 ? 1 : (CT_T == 16 && THREAD
 // block of rows holding local row rho at position bitrev_r(rho); the two steps simply swap their shared-memory access shapes.
 __device__ __forceinline__ void mbar_init(u32 bar, u32 count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
 __device__ __forceinline__ void mbar_wait(u32 bar, u32 parity) {
-    u32 done = 0;
-    while (!done)
+    u32 done = 0, spins = 0;
+    unsigned long long t0 = 0;
+    while (true) {
         asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (done) break;
+        // watchdog: a pass takes milliseconds; a wait of 20 s can only be a protocol error.  Trap (the launch fails with an error the
+        // host reports) instead of leaving a hung kernel on the device.
+        if ((++spins & 0xfffu) == 0) {
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 20000000000ull) __trap();
+        }
+    }
 }
 __device__ __forceinline__ void mbar_arrive(u32 bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
 __device__ __forceinline__ void mbar_arrive_n(u32 bar, u32 n) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(n) : "memory"); }
