@@ -82,3 +82,17 @@ def test_cpp_host_mirror_compiles_and_fails_loudly_without_gpu(tmp_path):
         assert r.returncode == 0, r.stdout + r.stderr
     else:
         assert r.returncode == 3 and "no CPU fallback" in r.stdout, r.stdout + r.stderr
+
+
+def test_device_arithmetic_source_on_the_host(tmp_path):
+    """csrc/field.cuh (the arithmetic every kernel is built from) compiled as plain C++ and run on the host: Montgomery and Shoup
+    multiplies, the lazy [0, 2p) butterfly contract for any 32-bit input, EF4 products and the two-adic generators, for both
+    fields, against 64-bit reference arithmetic (tests/cpp/device_math_check.cpp)."""
+    import os
+    import subprocess
+    cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
+    exe = tmp_path / "device_math_check"
+    subprocess.run(["/usr/bin/g++", "-std=c++17", "-O2", "-w", "-I", cuda_inc, str(ROOT / "tests" / "cpp" / "device_math_check.cpp"), "-o", str(exe)],
+                   check=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.count("ok ") == 2, r.stdout + r.stderr
