@@ -13,6 +13,7 @@
 
 #include "../../include/p3gpu.h"
 #include "field.cuh"
+#include "poseidon2_consts.h"
 
 namespace p3 {
 
@@ -41,13 +42,6 @@ void set_error(const char *fmt, ...);
         if (rc__ != P3GPU_OK) return rc__; \
     } while (0)
 
-struct Poseidon2Consts {          // device layout consumed by the hash kernels
-    u32 rc_ext[8 * 24];  // external round r (0-3 initial, 4-7 terminal), element i at r * width + i
-    u32 rc_int[32];
-    int rounds_p;
-    int width;
-    int set;
-};
 
 struct TwiddleKey {
     int field, log_n; u32 shift; int inverse;

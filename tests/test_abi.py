@@ -96,3 +96,42 @@ def test_device_arithmetic_source_on_the_host(tmp_path):
                    check=True)
     r = subprocess.run([str(exe)], capture_output=True, text=True)
     assert r.returncode == 0 and r.stdout.count("ok ") == 2, r.stdout + r.stderr
+
+
+def test_device_permutation_source_on_the_host(tmp_path):
+    """csrc/hash_core.cuh — the Poseidon2 (looped rounds, lazy S-box, shift-based diagonal) and Keccak-f (32-bit halves) device
+    functions the hash kernels are built from — compiled as plain C++ (tests/cpp/hash_core_host.cpp) and checked on the host:
+    the reference's Poseidon2 known-answer vectors, random states against the oracle, Keccak-f against the oracle (itself pinned
+    to FIPS-202)."""
+    import json
+    import os
+    import subprocess
+    import numpy as np
+    from oracle import p3_oracle as O
+    from plonky3_b200.field import BabyBear, KoalaBear
+    from plonky3_b200.poseidon2 import default_poseidon2
+    cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
+    exe = tmp_path / "hash_core_host"
+    subprocess.run(["/usr/bin/g++", "-std=c++17", "-O2", "-w", "-I", cuda_inc, str(ROOT / "tests" / "cpp" / "hash_core_host.cpp"), "-o", str(exe)], check=True)
+    kats = json.loads((ROOT / "tests" / "golden" / "poseidon2_kat.json").read_text())
+    jobs, expect = [], []
+    for f in (BabyBear, KoalaBear):
+        for w in (16, 24):
+            cfg = default_poseidon2(f, w)
+            kat = kats[f"{f.name}_{w}"]
+            states = np.vstack([O.to_monty_arr(f.id, kat["input"])[None, :], O.random_matrix(f.id, 40, w, seed=w + f.id)])
+            pm = O.default_perm(f.id, w)
+            want = np.vstack([O.poseidon2_permute(pm, s) for s in states])
+            assert O.from_monty_arr(f.id, want[0]).tolist() == kat["expected"]      # the oracle on the reference's vector
+            rc_ext = np.concatenate([cfg.rc_initial.ravel(), cfg.rc_terminal.ravel()])
+            jobs.append(" ".join(map(str, ["p2", f.id, w, len(cfg.rc_internal), *rc_ext.tolist(), *cfg.rc_internal.tolist(), len(states),
+                                           *states.ravel().tolist()])))
+            expect.append(want.ravel().astype(np.uint64))
+    kst = np.random.default_rng(5).integers(0, 1 << 63, size=(20, 25), dtype=np.uint64) * np.uint64(2) + np.uint64(1)
+    kst[0] = 0
+    jobs.append("keccak %d %s" % (len(kst), " ".join(map(str, kst.ravel().tolist()))))
+    expect.append(np.vstack([O.keccak_f(s) for s in kst]).ravel())
+    r = subprocess.run([str(exe)], input="\n".join(jobs) + "\n", capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    got = np.array(r.stdout.split(), dtype=np.uint64)
+    assert np.array_equal(got, np.concatenate(expect))
