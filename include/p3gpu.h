@@ -23,8 +23,10 @@
  *   - There is no CPU fallback: without a CUDA device p3gpu_ctx_create fails with P3GPU_ECUDA.
  *   - Threads and devices: a context belongs to one device and serialises its work on one stream; every entry point makes
  *     that device current for the calling host thread, so calls may come from any thread (the reference's DFT / MMCS
- *     objects are Clone + Sync).  One context must not be used by two threads at the same time; use one context per
- *     thread (each has its own stream, scratch buffers and twiddle cache) to keep several calls in flight.
+ *     objects are Clone + Sync, radix_2_dit_parallel.rs:32-40).  A context is RE-ENTRANT: every entry point holds the
+ *     context's internal mutex for its whole duration, so several threads may share one context (their calls are
+ *     serialised); use one context per thread (each has its own stream, scratch buffers and twiddle cache) to keep
+ *     several calls in flight.  The twiddle cache is bounded (LRU by bytes, P3GPU_TWIDDLE_CACHE_MB, default 2048).
  */
 #ifndef P3GPU_H
 #define P3GPU_H
@@ -100,6 +102,9 @@ int32_t p3gpu_dft_batch(p3gpu_ctx *ctx, int field, int kind, uint32_t *h_inout, 
  * d_out must not alias d_in. */
 int32_t p3gpu_coset_lde_batch_dev(p3gpu_ctx *ctx, int field, const uint32_t *d_in, size_t h, size_t w,
                                   unsigned added_bits, uint32_t shift, uint32_t *d_out, int bitrev_rows);
+/* Host-pointer variant: large calls are pipelined internally in column chunks on three streams — H2D(chunk i+1) || LDE(chunk i)
+ * || D2H(chunk i-1) — so ONE call approaches the PCIe floor max(H2D, D2H) (P3GPU_E2E_CHUNKS, default 4; page-lock the buffers
+ * with p3gpu_host_register for full rate). */
 int32_t p3gpu_coset_lde_batch(p3gpu_ctx *ctx, int field, const uint32_t *h_in, size_t h, size_t w,
                               unsigned added_bits, uint32_t shift, uint32_t *h_out, int bitrev_rows);
 
@@ -146,7 +151,11 @@ int32_t p3gpu_fri_fold(p3gpu_ctx *ctx, int field, const uint32_t *h_in, size_t r
  * (fri/src/prover.rs:258-265). */
 int32_t p3gpu_ef_axpy_dev(p3gpu_ctx *ctx, int field, uint32_t *d_acc, const uint32_t *d_x, size_t n, const uint32_t s[4]);
 
-/* commit_phase (fri/src/prover.rs:192-286) for ONE input vector with caller-supplied betas (the Fiat-Shamir
+/* BENCHMARK / TEST ONLY — not the Fiat-Shamir flow of fri/src/prover.rs:237-248: all betas are supplied up front, so no beta
+ * depends on the cap of its round, and a single input vector is supported (no roll-in of shorter inputs).  A prover
+ * drives the transcript per round: p3gpu_merkle_commit_dev -> cap to the host -> challenger -> p3gpu_fri_fold_dev
+ * (-> p3gpu_ef_axpy_dev for the roll-in); plonky3_b200.fri.commit_phase does exactly that and is what bench.py times.
+ * commit_phase (fri/src/prover.rs:192-286) for ONE input vector with caller-supplied betas (the Fiat-Shamir
  * transcript stays on the host; with commit_proof_of_work_bits = 0 a round's beta depends only on that round's cap,
  * so a host driving the transcript calls p3gpu_merkle_commit_dev / p3gpu_fri_fold_dev per round instead).
  * d_vec: len EF4 values (bit-reversed), consumed.  Rounds use compute_log_arity_for_round (fri/src/config.rs:180-207).
@@ -183,6 +192,62 @@ int32_t p3gpu_open_reduce_dev(p3gpu_ctx *ctx, int field, uint32_t *d_ro, const u
 int32_t p3gpu_pcs_commit_dev(p3gpu_ctx *ctx, int field, int hash, const uint32_t *d_evals, size_t h, size_t w,
                              unsigned log_blowup, uint32_t *d_lde, uint32_t *d_layers, size_t *layer_lens,
                              size_t *n_layers);
+
+/* The same commit with the trace in HOST memory (pinned for full PCIe rate): the realistic drop-in point of a GpuFriPcs (the
+ * reference's Pcs::commit receives host matrices, two_adic_pcs.rs:300-324).  The trace crosses PCIe once, in column chunks
+ * whose copies overlap the LDE of the previous chunk; LDE and digest layers stay resident in d_lde / d_layers; only the cap
+ * (2^min(cap_height, layers-1) digests) is copied back to h_cap.  Synchronous. */
+int32_t p3gpu_pcs_commit(p3gpu_ctx *ctx, int field, int hash, const uint32_t *h_evals, size_t h, size_t w, unsigned log_blowup,
+                         unsigned cap_height, uint32_t *d_lde, uint32_t *d_layers, size_t *layer_lens, size_t *n_layers,
+                         uint32_t *h_cap, size_t *cap_len);
+
+/* ---- multi-GPU: one process per GPU, peer memory over NVLink ------------------
+ * The path shards by COLUMN for the LDE (every column is an independent polynomial, dft/src/traits.rs:22-24) and by
+ * ROW RANGE for the Merkle tree (a leaf is a sequential sponge over the whole row, merkle_tree.rs:309-317; rows
+ * [k*H/G, (k+1)*H/G) of the bit-reversed LDE are a complete sub-tree).  The re-sharding all-to-all is fused into the
+ * LDE's last pass: its stores go straight into the destination rank's row block through CUDA-IPC-mapped peer pointers.
+ * No collective library is involved; the host only exchanges 64-byte IPC handles once (any channel: MPI, sockets,
+ * torch.distributed, ...) and fills a p3gpu_peer_group. */
+#define P3GPU_PEER_CTRL_BYTES 65536   /* size of every rank's control block (p3gpu_malloc'ed, zeroed, IPC-exported) */
+#define P3GPU_PEER_CTRL_USER 256      /* byte offset of its user area (all-gather tables); the first 64 bytes are barrier flags */
+typedef struct p3gpu_peer_group {
+    uint32_t world, rank;             /* ranks (power of two, <= 16), my rank */
+    void *ctrl[16];                   /* control block of every rank: own pointer at [rank], IPC-mapped pointers elsewhere */
+    uint32_t *rows[16];               /* row block of every rank: (H / world) x w_total u32, row-major (NULL if unused) */
+    double timeout_s;                 /* barrier watchdog (0 = 20 s): a missing peer traps the kernel instead of hanging */
+} p3gpu_peer_group;
+
+/* cudaIpcGetMemHandle / cudaIpcOpenMemHandle / cudaIpcCloseMemHandle on a p3gpu_malloc'ed buffer (64-byte handle) */
+int32_t p3gpu_ipc_export(p3gpu_ctx *ctx, void *dptr, uint8_t handle[64]);
+int32_t p3gpu_ipc_import(p3gpu_ctx *ctx, const uint8_t handle[64], void **dptr);
+int32_t p3gpu_ipc_close(p3gpu_ctx *ctx, void *dptr);
+int32_t p3gpu_memset_dev(p3gpu_ctx *ctx, void *dptr, int value, size_t bytes);
+
+/* Stream-ordered flag barrier across the group (system-scope release/acquire on the control blocks).  `epoch` must be
+ * the same on all ranks and strictly increasing from call to call (1, 2, 3, ...). */
+int32_t p3gpu_peer_barrier_dev(p3gpu_ctx *ctx, const p3gpu_peer_group *grp, uint32_t epoch);
+/* Every rank stores `words` u32 from d_src into slot `rank` of the table at user-area offset table_offset_bytes of EVERY
+ * rank's control block (replaces the all-gather of Merkle roots / FRI final polynomials; pair with a barrier). */
+int32_t p3gpu_peer_allgather_dev(p3gpu_ctx *ctx, const p3gpu_peer_group *grp, size_t table_offset_bytes, const uint32_t *d_src, size_t words);
+
+/* coset_lde_batch of this rank's column block [col_off, col_off + w_local) of a trace of width w_total; the
+ * bit-reversed-row result is scattered by row range: LDE row r goes to grp->rows[r / (H/world)] (local row r % (H/world),
+ * columns col_off.., pitch w_total).  Needs w_local % 4 == 0 (column blocks that are multiples of 8 keep every 32-byte
+ * store segment sector-aligned) and H / world >= 1024.  Complete on all ranks only after a following barrier. */
+int32_t p3gpu_coset_lde_batch_sharded_dev(p3gpu_ctx *ctx, int field, const p3gpu_peer_group *grp, const uint32_t *d_in, size_t h,
+                                          size_t w_local, unsigned added_bits, uint32_t shift, size_t w_total, size_t col_off);
+
+/* TwoAdicFriPcs::commit (two_adic_pcs.rs:300-324) of ONE trace sharded by column block over the group; bit-identical to
+ * the single-GPU commitment: sharded LDE (above) -> barrier -> leaf hashing + sub-tree over grp->rows[rank] -> exchange
+ * of the cap slices -> barrier -> (cap_height < log2(world): top levels compressed redundantly on every rank).
+ * *epoch: the group's barrier epoch counter (start at 0; same variable for every collective call of this group).
+ * d_sub_layers: p3gpu_merkle_total_digests(H / world) digests = this rank's sub-tree (kept for openings);
+ * h_cap: 2^cap_height digests (host), identical on every rank.  phase_ms (NULL or 4 floats): device time of
+ * [LDE + peer stores, barrier wait, hashing, cap exchange]. */
+int32_t p3gpu_commit_sharded_dev(p3gpu_ctx *ctx, int field, int hash, const p3gpu_peer_group *grp, uint32_t *epoch,
+                                 const uint32_t *d_evals_local, size_t h, size_t w_local, size_t w_total, size_t col_off,
+                                 unsigned log_blowup, unsigned cap_height, uint32_t *d_sub_layers, size_t *layer_lens,
+                                 size_t *n_layers, uint32_t *h_cap, size_t *cap_len, float *phase_ms);
 
 #ifdef __cplusplus
 }

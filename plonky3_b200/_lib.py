@@ -23,7 +23,17 @@ EXPORTS = [
     "p3gpu_merkle_total_digests", "p3gpu_merkle_commit_dev", "p3gpu_merkle_commit", "p3gpu_merkle_from_digests_dev",
     "p3gpu_fri_fold_dev", "p3gpu_fri_fold", "p3gpu_ef_axpy_dev", "p3gpu_fri_commit_phase_dev", "p3gpu_pcs_commit_dev",
     "p3gpu_open_inv_denoms_dev", "p3gpu_columnwise_dot_dev", "p3gpu_rowwise_dot_dev", "p3gpu_open_reduce_dev",
+    "p3gpu_pcs_commit", "p3gpu_ipc_export", "p3gpu_ipc_import", "p3gpu_ipc_close", "p3gpu_memset_dev", "p3gpu_peer_barrier_dev",
+    "p3gpu_peer_allgather_dev", "p3gpu_coset_lde_batch_sharded_dev", "p3gpu_commit_sharded_dev",
 ]
+
+PEER_CTRL_BYTES, PEER_CTRL_USER = 65536, 256
+
+
+class PeerGroupStruct(C.Structure):
+    """p3gpu_peer_group (include/p3gpu.h)."""
+    _fields_ = [("world", C.c_uint32), ("rank", C.c_uint32), ("ctrl", C.c_void_p * 16), ("rows", C.c_void_p * 16),
+                ("timeout_s", C.c_double)]
 
 
 class P3GpuError(RuntimeError):
@@ -76,6 +86,15 @@ def load():
         "p3gpu_rowwise_dot_dev": (i32, [vp, ci, vp, sz, sz, vp, vp]),
         "p3gpu_open_reduce_dev": (i32, [vp, ci, vp, vp, vp, sz, vp, vp]),
         "p3gpu_pcs_commit_dev": (i32, [vp, ci, ci, vp, sz, sz, cu, vp, vp, vp, vp]),
+        "p3gpu_pcs_commit": (i32, [vp, ci, ci, vp, sz, sz, cu, cu, vp, vp, vp, vp, vp, vp]),
+        "p3gpu_ipc_export": (i32, [vp, vp, vp]),
+        "p3gpu_ipc_import": (i32, [vp, vp, C.POINTER(vp)]),
+        "p3gpu_ipc_close": (i32, [vp, vp]),
+        "p3gpu_memset_dev": (i32, [vp, vp, ci, sz]),
+        "p3gpu_peer_barrier_dev": (i32, [vp, vp, u32]),
+        "p3gpu_peer_allgather_dev": (i32, [vp, vp, sz, vp, sz]),
+        "p3gpu_coset_lde_batch_sharded_dev": (i32, [vp, ci, vp, vp, sz, sz, cu, u32, sz, sz]),
+        "p3gpu_commit_sharded_dev": (i32, [vp, ci, ci, vp, vp, vp, sz, sz, sz, sz, cu, cu, vp, vp, vp, vp, vp, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)

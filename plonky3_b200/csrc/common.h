@@ -4,6 +4,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <tuple>
@@ -36,6 +37,14 @@ void set_error(const char *fmt, ...);
         }                                         \
     } while (0)
 
+// first statement of every extern "C" entry point that takes a context: serialise callers, select the device (CUDA's current
+// device is per host thread: callers may come from any thread)
+#define P3_ENTER(ctx)                                                        \
+    P3_CHECK((ctx) != nullptr, P3GPU_EINVAL, "null context");                \
+    std::lock_guard<std::recursive_mutex> p3_lock__((ctx)->call_mu);         \
+    P3_CUDA(cudaSetDevice((ctx)->device));                                   \
+    (ctx)->tick++
+
 #define P3_TRY(expr)                      \
     do {                                  \
         int32_t rc__ = (expr);            \
@@ -52,16 +61,30 @@ struct TwiddleKey {
 
 }  // namespace p3
 
+namespace p3 { struct TwiddleEntry { uint2 *ptr; size_t bytes; uint64_t last_use; }; }
+
 struct p3gpu_ctx {
     int device = 0;
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
+    cudaEvent_t switch_event = nullptr;   // orders work across p3gpu_ctx_set_stream changes (shared scratch / caches)
     int sm_count = 148;
     uint64_t launches = 0;
-    std::mutex mu;
-    // twiddle heaps keyed like the reference's coset_twiddles cache (radix_2_dit_parallel.rs:32-40)
-    std::map<p3::TwiddleKey, uint2 *> twiddles;
+    // Every extern "C" entry point holds call_mu for its whole duration: the reference's objects are Clone + Sync and may be
+    // called through &self from several threads (SURVEY 8b "Threading"); a context serialises such callers (scratch buffers,
+    // caches and the stream are per context).  Clones that want concurrency create their own context.
+    std::recursive_mutex call_mu;
+    uint64_t tick = 0;                    // entry-point counter: LRU clock of the twiddle cache
+    // twiddle heaps keyed like the reference's coset_twiddles cache (radix_2_dit_parallel.rs:32-40), bounded by bytes (LRU)
+    std::map<p3::TwiddleKey, p3::TwiddleEntry> twiddles;
     size_t twiddle_bytes = 0;
+    size_t twiddle_cap_bytes = (size_t)2 << 30;   // P3GPU_TWIDDLE_CACHE_MB
+    void *leaf_table = nullptr; size_t leaf_table_bytes = 0;
+    // host-pointer entry points: copy streams + events of the chunked H2D || compute || D2H pipeline, double-buffered chunk buffers
+    cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
+    cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr}, ev_start = nullptr;
+    void *chunk_in[2] = {nullptr, nullptr}; size_t chunk_in_bytes[2] = {0, 0};
+    void *chunk_out[2] = {nullptr, nullptr}; size_t chunk_out_bytes[2] = {0, 0};   // device copy of the per-height matrix table (> 8 matrices)
     // FRI half-inverse-power tables (bit-reversed), one per field, grown on demand
     uint32_t *fold_table[2] = {nullptr, nullptr};
     size_t fold_table_len[2] = {0, 0};
@@ -78,12 +101,13 @@ namespace p3 {
 
 int32_t ctx_scratch(p3gpu_ctx *ctx, size_t bytes, void **out);
 int32_t ctx_scratch2(p3gpu_ctx *ctx, size_t bytes, void **out);
-int32_t ctx_pool(p3gpu_ctx *ctx, int slot, size_t bytes, void **out);  // grow-only cached device buffers (no malloc/free per call)
+int32_t ctx_pool(p3gpu_ctx *ctx, int slot, size_t bytes, void **out);
+int32_t ctx_leaf_table(p3gpu_ctx *ctx, size_t bytes, void **out);  // grow-only cached device buffers (no malloc/free per call)
 
 // ntt.cu
 int32_t ntt_dft_batch(p3gpu_ctx *ctx, int field, int kind, const u32 *d_in, u32 *d_out, size_t h, size_t w, u32 shift);
 int32_t ntt_coset_lde(p3gpu_ctx *ctx, int field, const u32 *d_in, size_t h, size_t w, unsigned added_bits, u32 shift,
-                      u32 *d_out, int bitrev_rows);
+                      u32 *d_out, int bitrev_rows, size_t in_pitch = 0, size_t out_pitch = 0);
 // hash.cu
 int32_t hash_poseidon2_permute(p3gpu_ctx *ctx, int field, int width, u32 *d_states, size_t n);
 int32_t hash_keccak_f(p3gpu_ctx *ctx, u64 *d_states, size_t n);
@@ -102,6 +126,12 @@ int32_t open_inv_denoms(p3gpu_ctx *ctx, int field, unsigned log_h, const u32 *z,
 int32_t open_columnwise_dot(p3gpu_ctx *ctx, int field, const u32 *d_mat, size_t h, size_t w, const u32 *d_vec, u32 *d_out, const u32 *scale);
 int32_t open_rowwise_dot(p3gpu_ctx *ctx, int field, const u32 *d_mat, size_t h, size_t w, const u32 *alpha, u32 *d_out);
 int32_t open_reduce(p3gpu_ctx *ctx, int field, u32 *d_ro, const u32 *d_r, const u32 *d_invd, size_t h, const u32 *coeff, const u32 *yred);
+
+// ntt.cu / peer.cu: multi-GPU
+int32_t ntt_coset_lde_sharded(p3gpu_ctx *ctx, int field, const u32 *d_in, size_t h, size_t w_local, unsigned added_bits, u32 shift,
+                              unsigned world, u32 *const *rank_out, size_t w_total, size_t col_off);
+int32_t peer_barrier(p3gpu_ctx *ctx, unsigned world, unsigned rank, void *const *ctrl, u32 epoch, double timeout_s);
+int32_t peer_allgather(p3gpu_ctx *ctx, unsigned world, unsigned rank, void *const *tables, const u32 *d_src, size_t words);
 
 static inline unsigned log2_floor(size_t x) { unsigned l = 0; while ((x >> l) > 1) l++; return l; }
 static inline bool is_pow2(size_t x) { return x && !(x & (x - 1)); }

@@ -32,25 +32,32 @@ __global__ void __launch_bounds__(128) poseidon2_permute_kernel(u32 *states, siz
 }
 
 // ---- leaf sponge ---------------------------------------------------------------------------------
-constexpr int MAX_MATS = 8;
+// The matrices of one height class (any number: merkle_tree.rs:131-133,312-316 has no limit).  Up to MAX_INLINE_MATS travel
+// inside the kernel parameters (constant-bank operands); larger batches (commit_quotient with many chunks, batch-STARK style
+// commits, one piece per source rank in the row-sharded multi-GPU commit) pass the table through device memory.
+constexpr int MAX_INLINE_MATS = 8;
 struct LeafArgs {
-    const u32 *ptr[MAX_MATS];
-    u32 width[MAX_MATS];
+    const u32 *ptr[MAX_INLINE_MATS];
+    u32 width[MAX_INLINE_MATS];
     int n_mats;
     size_t height;
     u32 *out;  // height x 8
+    const u32 *const *dev_ptr;   // n_mats > MAX_INLINE_MATS: device arrays of n_mats pointers / widths, else null
+    const u32 *dev_width;
+    __device__ __forceinline__ const u32 *mat(int m) const { return dev_ptr ? dev_ptr[m] : ptr[m]; }
+    __device__ __forceinline__ u32 wid(int m) const { return dev_ptr ? dev_width[m] : width[m]; }
 };
 
 // streaming cursor over the concatenation of row r of every matrix (input order; merkle_tree.rs:312-316)
 struct RowCursor {
-    const LeafArgs &a; size_t row; int m; u32 col; const u32 *p;
-    __device__ __forceinline__ RowCursor(const LeafArgs &a_, size_t r) : a(a_), row(r), m(0), col(0), p(nullptr) { settle(); }
+    const LeafArgs &a; size_t row; int m; u32 col, w; const u32 *p;
+    __device__ __forceinline__ RowCursor(const LeafArgs &a_, size_t r) : a(a_), row(r), m(0), col(0), w(0), p(nullptr) { settle(); }
     __device__ __forceinline__ void settle() {
-        while (m < a.n_mats && col >= a.width[m]) { m++; col = 0; }
-        if (m < a.n_mats) p = a.ptr[m] + row * a.width[m];
+        while (m < a.n_mats && col >= (w = a.wid(m))) { m++; col = 0; }
+        if (m < a.n_mats) p = a.mat(m) + row * w;
     }
     __device__ __forceinline__ bool more() const { return m < a.n_mats; }
-    __device__ __forceinline__ u32 next() { u32 v = __ldg(p + col); col++; if (col >= a.width[m]) settle(); return v; }
+    __device__ __forceinline__ u32 next() { u32 v = __ldg(p + col); col++; if (col >= w) settle(); return v; }
 };
 
 template <int F, int W>
@@ -278,17 +285,33 @@ int32_t hash_merkle_commit(p3gpu_ctx *ctx, int field, int hash, size_t n_mats, c
     std::stable_sort(order.begin(), order.end(), [&](size_t x, size_t y) { return heights[x] > heights[y]; });
     const size_t max_h = heights[order[0]];
 
+    // device table for height classes with more than MAX_INLINE_MATS matrices: [n pointers][n widths] per class, every class
+    // of this call in its own slice of one grow-only context buffer (classes of one call must not overwrite each other:
+    // their kernels are only stream-ordered)
+    size_t table_off = 0;
+    void *table = nullptr;
+    P3_TRY(ctx_leaf_table(ctx, n_mats * 16 + 64, &table));
     auto fill_leaf = [&](size_t begin, size_t end, size_t h, u32 *out, LeafArgs &la) -> int32_t {
-        P3_CHECK(end - begin <= (size_t)MAX_MATS, P3GPU_EUNSUPPORTED, "more than %d matrices of one height in a batch", MAX_MATS);
         memset(&la, 0, sizeof la);
-        la.n_mats = 0;
+        std::vector<const u32 *> ps;
+        std::vector<u32> ws;
         for (size_t k = begin; k < end; k++) {
             if (widths[order[k]] == 0) continue;  // contributes nothing to the stream
-            la.ptr[la.n_mats] = d_mats[order[k]];
-            la.width[la.n_mats] = (u32)widths[order[k]];
-            la.n_mats++;
+            ps.push_back(d_mats[order[k]]);
+            ws.push_back((u32)widths[order[k]]);
         }
+        la.n_mats = (int)ps.size();
         la.height = h; la.out = out;
+        if (ps.size() <= (size_t)MAX_INLINE_MATS) {
+            for (size_t k = 0; k < ps.size(); k++) { la.ptr[k] = ps[k]; la.width[k] = ws[k]; }
+            return P3GPU_OK;
+        }
+        unsigned char *base = (unsigned char *)table + table_off;
+        P3_CUDA(cudaMemcpyAsync(base, ps.data(), ps.size() * 8, cudaMemcpyHostToDevice, ctx->stream));           // pageable source: staged before return
+        P3_CUDA(cudaMemcpyAsync(base + ps.size() * 8, ws.data(), ws.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+        la.dev_ptr = reinterpret_cast<const u32 *const *>(base);
+        la.dev_width = reinterpret_cast<const u32 *>(base + ps.size() * 8);
+        table_off += (ps.size() * 12 + 15) & ~(size_t)15;
         return P3GPU_OK;
     };
 

@@ -75,6 +75,13 @@ struct PassArgs {
     size_t tw_stride;   // uint2 elements between consecutive cosets' heaps
     size_t out_stride;  // u32 elements between consecutive cosets' output blocks
     size_t in_stride;   // u32 elements between consecutive cosets' input blocks
+    // Row-sharded output over peer memory (multi-GPU commit, last pass of the LDE only; pipelined kernel, dense output):
+    // LDE row (coset << log_n) + i belongs to rank row >> shard_log_rows and is stored at that rank's buffer
+    // shard_out[rank] (already offset to this launch's first column), local row = row & (2^shard_log_rows - 1), pitch w.
+    // The buffers are this GPU's own block plus the peers' blocks mapped through CUDA IPC: the all-to-all that re-shards
+    // column blocks into row blocks happens in the pass's own stores, tile by tile, over NVLink.
+    u32 *shard_out[16];
+    int shard_log_rows;   // 0 = off
 };
 
 template <int LOG_CT> __device__ __forceinline__ u32 sidx(u32 row, u32 c) {
@@ -651,6 +658,10 @@ __global__ void __launch_bounds__(NGROUP * GTHREADS + 32, 1) ntt_pass_pipe_kerne
                     const u32 i0 = ibase | (gg << (lowbits + Q2));
                     const u32 row0 = ((a.out_bitrev ? (__brev(i0) >> brsh) : i0) << a.out_sh) + a.out_add;
                     u32 *p = out + (size_t)row0 * ow + c;
+                    if (a.shard_log_rows) {   // peer-memory row sharding (dense, natural network order: a tile's rows are contiguous)
+                        const u32 grow = (coset << a.log_n) + row0;
+                        p = a.shard_out[grow >> a.shard_log_rows] + (size_t)(grow & ((1u << a.shard_log_rows) - 1u)) * ow + col + c;
+                    }
                     if (a.out_bitrev) {
 #pragma unroll
                         for (u32 m = 0; m < E2; m++) p[brev_const<Q2>(m) * sstride] = x[m];
@@ -712,14 +723,30 @@ __global__ void broadcast_row(const u32 *in, u32 *out, size_t rows, size_t w) {
 template <int F>
 static int32_t get_twiddles(p3gpu_ctx *ctx, int log_n, int added_bits, u32 shift, int inverse, const uint2 **out) {
     TwiddleKey key{F, log_n, shift, inverse + 2 * added_bits};
+    std::lock_guard<std::recursive_mutex> g(ctx->call_mu);   // entry points already hold it; kept for internal callers
     {
-        std::lock_guard<std::mutex> g(ctx->mu);
         auto it = ctx->twiddles.find(key);
-        if (it != ctx->twiddles.end()) { *out = it->second; return P3GPU_OK; }
+        if (it != ctx->twiddles.end()) { it->second.last_use = ctx->tick; *out = it->second.ptr; return P3GPU_OK; }
     }
     const size_t N = (size_t)1 << log_n, n_cosets = (size_t)1 << added_bits;
+    const size_t bytes = n_cosets * N * sizeof(uint2);
+    // bounded cache (the reference's map grows without bound; a long-lived prover with many shifts/sizes must not): evict
+    // least-recently-used heaps that no call of the current entry point has touched until the new heap fits
+    while (ctx->twiddle_bytes + bytes > ctx->twiddle_cap_bytes) {
+        auto victim = ctx->twiddles.end();
+        for (auto it = ctx->twiddles.begin(); it != ctx->twiddles.end(); ++it)
+            if (it->second.last_use < ctx->tick && (victim == ctx->twiddles.end() || it->second.last_use < victim->second.last_use)) victim = it;
+        if (victim == ctx->twiddles.end()) break;          // everything left is in use by this call: exceed the cap rather than fail
+        P3_CUDA(cudaStreamSynchronize(ctx->stream));       // queued kernels may still read the heap
+        P3_CUDA(cudaFree(victim->second.ptr));
+        ctx->twiddle_bytes -= victim->second.bytes;
+        ctx->twiddles.erase(victim);
+    }
     uint2 *Z = nullptr;
-    P3_CUDA(cudaMalloc(&Z, n_cosets * N * sizeof(uint2)));
+    {
+        cudaError_t e = cudaMalloc(&Z, bytes);
+        if (e != cudaSuccess) { set_error("cudaMalloc(%zu) for a twiddle heap failed: %s", bytes, cudaGetErrorString(e)); cudaGetLastError(); return P3GPU_ENOMEM; }
+    }
     const u32 g_big = two_adic_generator<F>((u32)(log_n + added_bits));
     for (size_t cb = 0; cb < n_cosets; cb++) {
         size_t c = 0;
@@ -729,18 +756,17 @@ static int32_t get_twiddles(p3gpu_ctx *ctx, int log_n, int added_bits, u32 shift
         for (int l = 0; l < 32; l++) { a.sigma[l] = Fp<F>::ONE; a.roots[l] = Fp<F>::ONE; }
         for (int l = 0; l < log_n; l++) a.sigma[l] = fp_pow<F>(s, (u64)(N >> (l + 1)));
         for (u32 k = 0; k <= (u32)log_n && k <= Fp<F>::TWO_ADICITY; k++) {
-            u32 g = two_adic_generator<F>(k);
-            a.roots[k] = inverse ? fp_inv<F>(g) : g;
+            u32 gk = two_adic_generator<F>(k);
+            a.roots[k] = inverse ? fp_inv<F>(gk) : gk;
         }
         const unsigned blocks = (unsigned)((N + 255) / 256);
         gen_twiddle_heap<F><<<blocks, 256, 0, ctx->stream>>>(Z + cb * N, log_n, a);
         ctx->launches++;
-        P3_CUDA(cudaGetLastError());
+        const cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) { cudaFree(Z); set_error("gen_twiddle_heap launch failed: %s", cudaGetErrorString(e)); return P3GPU_ECUDA; }
     }
-    std::lock_guard<std::mutex> g(ctx->mu);
-    auto ins = ctx->twiddles.emplace(key, Z);
-    if (!ins.second) { cudaFree(Z); Z = ins.first->second; }  // lost a race: keep the first table
-    else ctx->twiddle_bytes += n_cosets * N * sizeof(uint2);
+    ctx->twiddles.emplace(key, TwiddleEntry{Z, bytes, ctx->tick});
+    ctx->twiddle_bytes += bytes;
     *out = Z;
     return P3GPU_OK;
 }
@@ -993,6 +1019,12 @@ static int32_t launch_pass(p3gpu_ctx *ctx, PassArgs a, unsigned n_cosets, int ma
     return P3GPU_OK;
 }
 
+struct ShardedOut {
+    unsigned world, log_rows;       // ranks; log2 of the rows per rank (LDE height / world)
+    u32 *out[16];                   // per rank: its (rows x w_total) row-major block (own memory or an IPC-mapped peer)
+    size_t w_total, col_off;        // pitch of those blocks; first column this rank's column block occupies in them
+};
+
 struct NetworkPlan {
     int n_passes;
     int bounds[8];  // layer boundaries: pass k covers [bounds[k], bounds[k+1])
@@ -1087,7 +1119,11 @@ static int32_t dft_batch_impl(p3gpu_ctx *ctx, int kind, const u32 *d_in, u32 *d_
 //   inverse:  d_in (dense) --pass--> A (tiled) --passes in place--> A = coefficients, network order, lazy range
 //   forward:  A --PERM pass, per coset--> B (tiled, 2^added_bits blocks per tile) --passes in place--> last pass --> d_out (dense)
 template <int F>
-static int32_t lde_tiled_impl(p3gpu_ctx *ctx, const u32 *d_in, size_t h, size_t w, unsigned added_bits, u32 shift, u32 *d_out, bool *done) {
+static int32_t lde_tiled_impl(p3gpu_ctx *ctx, const u32 *d_in, size_t h, size_t w, unsigned added_bits, u32 shift, u32 *d_out, bool *done,
+                              const ShardedOut *shard = nullptr, size_t in_pitch = 0, size_t out_pitch = 0) {
+    // in_pitch / out_pitch (elements, 0 = w): the matrix may be a column block of a wider row-major buffer on either side
+    if (in_pitch == 0) in_pitch = w;
+    if (out_pitch == 0) out_pitch = w;
     *done = false;
     const int log_n = (int)log2_floor(h);
     const int max_r = std::min(10, std::max(6, env_int("P3GPU_NTT_MAXR", 10)));
@@ -1098,8 +1134,8 @@ static int32_t lde_tiled_impl(p3gpu_ctx *ctx, const u32 *d_in, size_t h, size_t 
         const int r = plan.bounds[k + 1] - plan.bounds[k];
         if (r < 6 || r > 10) return P3GPU_OK;
     }
-    if (w % 4 != 0 || w < 8 || (reinterpret_cast<uintptr_t>(d_in) | reinterpret_cast<uintptr_t>(d_out)) % 16 != 0) return P3GPU_OK;
-    if (((w * 4) << log_n) >= (1ull << 40) || tensor_map_encoder() == nullptr) return P3GPU_OK;
+    if (w % 4 != 0 || w < 8 || (reinterpret_cast<uintptr_t>(d_in) | reinterpret_cast<uintptr_t>(shard ? nullptr : d_out)) % 16 != 0) return P3GPU_OK;
+    if (((in_pitch * 4) << log_n) >= (1ull << 40) || in_pitch % 4 != 0 || tensor_map_encoder() == nullptr) return P3GPU_OK;
     const size_t n_cosets = (size_t)1 << added_bits;
     // column chunk: keep B (n_cosets * h * chunk * 4 bytes) around 1 GiB, at least 64 columns
     size_t chunk = ((size_t)1 << 28) / (n_cosets * h);
@@ -1125,7 +1161,7 @@ static int32_t lde_tiled_impl(p3gpu_ctx *ctx, const u32 *d_in, size_t h, size_t 
             memset(&a, 0, sizeof a);
             const int kk = plan.n_passes - 1 - k;            // reversed plan: bounds mirrored
             a.l0 = log_n - plan.bounds[kk + 1]; a.l1 = log_n - plan.bounds[kk];
-            a.w = (u32)w; a.wc = (u32)wc; a.log_n = log_n; a.n_cosets = 1; a.in_blocks = 1;
+            a.w = (u32)in_pitch; a.wc = (u32)wc; a.log_n = log_n; a.n_cosets = 1; a.in_blocks = 1;
             a.tw = tw_inv; a.tw_stride = 0;
             if (k == 0) { a.in = d_in + col0; a.in_tiled = 0; a.has_scale = 1; a.scale = inv_height_scale<F>(h); }
             else { a.in = (const u32 *)A; a.in_tiled = 1; }
@@ -1136,11 +1172,18 @@ static int32_t lde_tiled_impl(p3gpu_ctx *ctx, const u32 *d_in, size_t h, size_t 
             PassArgs a;
             memset(&a, 0, sizeof a);
             a.l0 = plan.bounds[k]; a.l1 = plan.bounds[k + 1];
-            a.w = (u32)w; a.wc = (u32)wc; a.log_n = log_n; a.n_cosets = (u32)n_cosets;
+            a.w = (u32)out_pitch; a.wc = (u32)wc; a.log_n = log_n; a.n_cosets = (u32)n_cosets;
             a.tw = tw; a.tw_stride = h;
             if (k == 0) { a.in = (const u32 *)A; a.in_tiled = 1; a.in_blocks = 1; a.in_bitrev = 1; }
             else { a.in = (const u32 *)B; a.in_tiled = 1; a.in_blocks = (u32)n_cosets; }
-            if (k == plan.n_passes - 1) { a.out = d_out + col0; a.out_tiled = 0; a.out_stride = h * w; a.final_reduce = 1; }
+            if (k == plan.n_passes - 1 && shard) {
+                // the last pass stores straight into the row blocks of all ranks (peer memory): pitch = the full trace width
+                a.out = nullptr; a.out_tiled = 0; a.final_reduce = 1;
+                a.w = (u32)shard->w_total;
+                a.shard_log_rows = (int)shard->log_rows;
+                for (unsigned g = 0; g < shard->world; g++) a.shard_out[g] = shard->out[g] + shard->col_off + col0;
+            }
+            else if (k == plan.n_passes - 1) { a.out = d_out + col0; a.out_tiled = 0; a.out_stride = h * out_pitch; a.final_reduce = 1; }
             else { a.out = (u32 *)B; a.out_tiled = 1; }
             P3_TRY(launch_pipe<F>(ctx, a));
         }
@@ -1151,7 +1194,7 @@ static int32_t lde_tiled_impl(p3gpu_ctx *ctx, const u32 *d_in, size_t h, size_t 
 
 template <int F>
 static int32_t coset_lde_impl(p3gpu_ctx *ctx, const u32 *d_in, size_t h, size_t w, unsigned added_bits, u32 shift, u32 *d_out,
-                              int bitrev_rows) {
+                              int bitrev_rows, size_t in_pitch = 0, size_t out_pitch = 0) {
     const int log_n = (int)log2_floor(h);
     const size_t n_cosets = (size_t)1 << added_bits;
     if (log_n == 0) {  // a constant polynomial: every evaluation equals the single input row
@@ -1163,9 +1206,11 @@ static int32_t coset_lde_impl(p3gpu_ctx *ctx, const u32 *d_in, size_t h, size_t 
     }
     if (bitrev_rows) {
         bool done = false;
-        P3_TRY(lde_tiled_impl<F>(ctx, d_in, h, w, added_bits, shift, d_out, &done));
+        P3_TRY(lde_tiled_impl<F>(ctx, d_in, h, w, added_bits, shift, d_out, &done, nullptr, in_pitch, out_pitch));
         if (done) return P3GPU_OK;
     }
+    P3_CHECK((in_pitch == 0 || in_pitch == w) && (out_pitch == 0 || out_pitch == w), P3GPU_EUNSUPPORTED,
+             "column-block LDE (pitch != width) needs the pipelined tiled path: bit-reversed rows, width %% 4 == 0, width >= 8, height >= 2^12");
     // 1) inverse network: evaluations on H (natural) -> coefficients in network (bit-reversed) order, scaled by 1/h
     const uint2 *tw_inv = nullptr;
     P3_TRY(get_twiddles<F>(ctx, log_n, 0, Fp<F>::ONE, 1, &tw_inv));
@@ -1214,12 +1259,35 @@ int32_t ntt_dft_batch(p3gpu_ctx *ctx, int field, int kind, const u32 *d_in, u32 
 }
 
 int32_t ntt_coset_lde(p3gpu_ctx *ctx, int field, const u32 *d_in, size_t h, size_t w, unsigned added_bits, u32 shift, u32 *d_out,
-                      int bitrev_rows) {
+                      int bitrev_rows, size_t in_pitch, size_t out_pitch) {
     P3_CHECK(added_bits <= 8, P3GPU_EINVAL, "added_bits %u too large", added_bits);
     P3_TRY(check_shape(field, h, w, added_bits));
     P3_CHECK(d_in != d_out, P3GPU_EINVAL, "coset_lde_batch cannot run in place");
-    return field == BABY_BEAR ? coset_lde_impl<BABY_BEAR>(ctx, d_in, h, w, added_bits, shift, d_out, bitrev_rows)
-                              : coset_lde_impl<KOALA_BEAR>(ctx, d_in, h, w, added_bits, shift, d_out, bitrev_rows);
+    P3_CHECK((in_pitch == 0 || in_pitch >= w) && (out_pitch == 0 || out_pitch >= w), P3GPU_EINVAL, "row pitch smaller than the width");
+    return field == BABY_BEAR ? coset_lde_impl<BABY_BEAR>(ctx, d_in, h, w, added_bits, shift, d_out, bitrev_rows, in_pitch, out_pitch)
+                              : coset_lde_impl<KOALA_BEAR>(ctx, d_in, h, w, added_bits, shift, d_out, bitrev_rows, in_pitch, out_pitch);
+}
+
+// Column-sharded coset LDE whose result lands row-sharded on all ranks (column blocks -> all-to-all -> row blocks).
+int32_t ntt_coset_lde_sharded(p3gpu_ctx *ctx, int field, const u32 *d_in, size_t h, size_t w_local, unsigned added_bits, u32 shift,
+                              unsigned world, u32 *const *rank_out, size_t w_total, size_t col_off) {
+    P3_CHECK(added_bits <= 8, P3GPU_EINVAL, "added_bits %u too large", added_bits);
+    P3_TRY(check_shape(field, h, w_local, added_bits));
+    P3_CHECK(world >= 1 && world <= 16 && (world & (world - 1)) == 0, P3GPU_EINVAL, "world size %u must be a power of two <= 16", world);
+    P3_CHECK(col_off + w_local <= w_total && w_total < (1ull << 31), P3GPU_EINVAL, "column block [%zu, %zu) outside the trace width %zu", col_off, col_off + w_local, w_total);
+    const size_t H = h << added_bits;
+    P3_CHECK(H % world == 0, P3GPU_EINVAL, "LDE height %zu not divisible by %u ranks", H, world);
+    ShardedOut sh;
+    memset(&sh, 0, sizeof sh);
+    sh.world = world; sh.log_rows = log2_floor(H / world); sh.w_total = w_total; sh.col_off = col_off;
+    // a tile of the last pass (2^r consecutive rows, r <= 10) must not straddle two ranks
+    P3_CHECK(sh.log_rows >= 10 && sh.log_rows <= 31, P3GPU_EUNSUPPORTED, "sharded LDE needs at least 1024 rows per rank (have 2^%u)", sh.log_rows);
+    for (unsigned g = 0; g < world; g++) { P3_CHECK(rank_out[g] != nullptr, P3GPU_EINVAL, "null output block for rank %u", g); sh.out[g] = rank_out[g]; }
+    bool done = false;
+    if (field == BABY_BEAR) P3_TRY(lde_tiled_impl<BABY_BEAR>(ctx, d_in, h, w_local, added_bits, shift, nullptr, &done, &sh));
+    else P3_TRY(lde_tiled_impl<KOALA_BEAR>(ctx, d_in, h, w_local, added_bits, shift, nullptr, &done, &sh));
+    P3_CHECK(done, P3GPU_EUNSUPPORTED, "sharded LDE needs the pipelined tiled path: width %% 4 == 0, width >= 8, 16-byte aligned input, 2^12 <= height");
+    return P3GPU_OK;
 }
 
 }  // namespace p3

@@ -24,11 +24,17 @@ import torch
 import torch.distributed as dist
 
 
-def column_block(width: int, world: int, rank: int):
-    """Contiguous column block of `rank`: the first width % world ranks get one extra column."""
-    base, extra = divmod(width, world)
-    start = rank * base + min(rank, extra)
-    return start, start + base + (1 if rank < extra else 0)
+def column_block(width: int, world: int, rank: int, align: int = 1):
+    """Contiguous column block of `rank` in units of `align` columns: the first (width/align) % world ranks get one extra
+    unit, the last rank also takes the width % align remainder.  align = 8 keeps every 32-byte segment the LDE's last pass
+    stores into a row block sector-aligned."""
+    units, rem = divmod(width, align)
+    base, extra = divmod(units, world)
+    start = (rank * base + min(rank, extra)) * align
+    stop = start + (base + (1 if rank < extra else 0)) * align
+    if rank == world - 1:
+        stop += rem
+    return start, stop
 
 
 class GpuBackend:
@@ -106,3 +112,139 @@ def commit_bit_exact(backend, evals_local: torch.Tensor, widths: List[int], cap_
         piece = layers[len(layers) - 1 - eff][: 1 << eff].contiguous()
         cap = torch.cat(_all_gather(piece, group))
     return cap, recv, layers
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Peer-memory mode: no collective library on the data path (csrc/peer.cu, include/p3gpu.h "multi-GPU")
+# ------------------------------------------------------------------------------------------------------------------
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import check
+
+
+class RawBuffer:
+    """Device memory from p3gpu_malloc (plain cudaMalloc: exportable through CUDA IPC, unlike a slice of torch's caching
+    allocator).  `tensor(shape)` views it as a CUDA int32 tensor without copying."""
+
+    def __init__(self, gpu, nbytes: int):
+        self.gpu, self.nbytes = gpu, int(nbytes)
+        p = C.c_void_p()
+        check(gpu.L.p3gpu_malloc(gpu.h, self.nbytes, C.byref(p)))
+        self.ptr = p.value
+
+    def tensor(self, shape):
+        n = int(np.prod(shape))
+        assert n * 4 <= self.nbytes
+        holder = type("_CudaArray", (), {})()
+        holder.__cuda_array_interface__ = {"shape": tuple(int(x) for x in shape), "typestr": "<i4", "data": (self.ptr, False), "version": 3}
+        holder._keepalive = self
+        return torch.as_tensor(holder, device=f"cuda:{self.gpu.device}")
+
+    def free(self):
+        if self.ptr:
+            check(self.gpu.L.p3gpu_free(self.gpu.h, C.c_void_p(self.ptr)))
+            self.ptr = None
+
+
+class PeerGroup:
+    """One rank's view of the group: its control block and row block plus every peer's, mapped through CUDA IPC.
+
+    rows_per_rank x w_total is the shape of the row block each rank hashes (rows_per_rank = LDE height / world).
+    Bootstrap = one all_gather_object of two 64-byte IPC handles per rank over torch.distributed (host side, once);
+    afterwards no collective library call is made on the data path."""
+
+    def __init__(self, gpu, rows_per_rank: int, w_total: int, group=None, timeout_s: float = 20.0, _sim=None):
+        self.gpu, self.rows_per_rank, self.w_total = gpu, int(rows_per_rank), int(w_total)
+        self.epoch = C.c_uint32(0)
+        self._imported = []
+        if _sim is not None:                       # single-process simulation (tests): all blocks live on this device
+            self.world, self.rank, self.ctrl, self.rows, peers = _sim
+        else:
+            self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+            self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+            self.ctrl = RawBuffer(gpu, _lib.PEER_CTRL_BYTES)
+            self.rows = RawBuffer(gpu, self.rows_per_rank * self.w_total * 4)
+            check(gpu.L.p3gpu_ctx_use_own_stream(gpu.h))
+            check(gpu.L.p3gpu_memset_dev(gpu.h, C.c_void_p(self.ctrl.ptr), 0, _lib.PEER_CTRL_BYTES))
+            gpu.sync()
+            peers = [(self.ctrl.ptr, self.rows.ptr)] * self.world
+            if self.world > 1:
+                hc, hr = (C.c_uint8 * 64)(), (C.c_uint8 * 64)()
+                check(gpu.L.p3gpu_ipc_export(gpu.h, C.c_void_p(self.ctrl.ptr), hc))
+                check(gpu.L.p3gpu_ipc_export(gpu.h, C.c_void_p(self.rows.ptr), hr))
+                handles = [None] * self.world
+                dist.all_gather_object(handles, (bytes(hc), bytes(hr)), group=group)
+                peers = []
+                for q, (bc, br) in enumerate(handles):
+                    if q == self.rank:
+                        peers.append((self.ctrl.ptr, self.rows.ptr))
+                        continue
+                    pc, pr = C.c_void_p(), C.c_void_p()
+                    check(gpu.L.p3gpu_ipc_import(gpu.h, (C.c_uint8 * 64).from_buffer_copy(bc), C.byref(pc)))
+                    check(gpu.L.p3gpu_ipc_import(gpu.h, (C.c_uint8 * 64).from_buffer_copy(br), C.byref(pr)))
+                    self._imported += [pc.value, pr.value]
+                    peers.append((pc.value, pr.value))
+                dist.barrier(group=group)          # every control block is zeroed and mapped before the first device barrier
+        self.struct = _lib.PeerGroupStruct()
+        self.struct.world, self.struct.rank, self.struct.timeout_s = self.world, self.rank, timeout_s
+        for q, (pc, pr) in enumerate(peers):
+            self.struct.ctrl[q], self.struct.rows[q] = pc, pr
+
+    @classmethod
+    def simulate(cls, gpus, rows_per_rank: int, w_total: int, timeout_s: float = 10.0):
+        """`len(gpus)` ranks inside ONE process on ONE device (one libp3gpu context = one stream per rank): lets a 1-GPU box
+        exercise the sharded kernels, the barrier and the all-gather bit for bit.  Ranks must be driven from separate host
+        threads, each under its own torch.cuda.stream (the barrier kernel spins until every rank has arrived: two ranks on
+        one stream would dead-lock until the watchdog fires)."""
+        world = len(gpus)
+        ctrl = [RawBuffer(g, _lib.PEER_CTRL_BYTES) for g in gpus]
+        rows = [RawBuffer(g, rows_per_rank * w_total * 4) for g in gpus]
+        for g, c in zip(gpus, ctrl):
+            check(g.L.p3gpu_ctx_use_own_stream(g.h))
+            check(g.L.p3gpu_memset_dev(g.h, C.c_void_p(c.ptr), 0, _lib.PEER_CTRL_BYTES))
+            g.sync()
+        peers = [(c.ptr, r.ptr) for c, r in zip(ctrl, rows)]
+        return [cls(g, rows_per_rank, w_total, timeout_s=timeout_s, _sim=(world, q, ctrl[q], rows[q], peers)) for q, g in enumerate(gpus)]
+
+    def rows_tensor(self):
+        return self.rows.tensor((self.rows_per_rank, self.w_total))
+
+    def barrier(self):
+        self.gpu._use_torch_stream()
+        self.epoch.value += 1
+        check(self.gpu.L.p3gpu_peer_barrier_dev(self.gpu.h, C.byref(self.struct), self.epoch.value))
+
+    def lde_sharded(self, field, evals_local, added_bits: int, shift: int, col_off: int):
+        """p3gpu_coset_lde_batch_sharded_dev on torch's current stream (complete on all ranks after the next barrier)."""
+        m = self.gpu._dev(evals_local); self.gpu._use_torch_stream()
+        check(self.gpu.L.p3gpu_coset_lde_batch_sharded_dev(self.gpu.h, field.id, C.byref(self.struct), m.data_ptr(), m.shape[0], m.shape[1],
+                                                          added_bits, shift, self.w_total, col_off))
+
+    def commit(self, field, hash_kind: int, evals_local, col_off: int, log_blowup: int, cap_height: int, phases: bool = False):
+        """p3gpu_commit_sharded_dev.  Returns (cap (n, 8) uint32 array — identical on every rank, my sub-tree's digest
+        layers as CUDA tensors, [lde_ms, barrier_ms, hash_ms, cap_exchange_ms] or None)."""
+        gpu = self.gpu
+        m = gpu._dev(evals_local)
+        h, w_local = int(m.shape[0]), int(m.shape[1])
+        assert (h << log_blowup) == self.rows_per_rank * self.world
+        gpu._use_torch_stream()
+        tot = gpu.merkle_total_digests(self.rows_per_rank)
+        layers = gpu._empty((tot, 8))
+        lens = (C.c_size_t * 65)(); nl = C.c_size_t()
+        cap = np.zeros((max(1 << cap_height, self.world), 8), dtype=np.uint32); cap_len = C.c_size_t()
+        ph = (C.c_float * 4)() if phases else None
+        check(gpu.L.p3gpu_commit_sharded_dev(gpu.h, field.id, hash_kind, C.byref(self.struct), C.byref(self.epoch), m.data_ptr(), h, w_local,
+                                             self.w_total, col_off, log_blowup, cap_height, layers.data_ptr(), lens, C.byref(nl),
+                                             cap.ctypes.data, C.byref(cap_len), ph))
+        out, off = [], 0
+        for k in range(nl.value):
+            out.append(layers[off:off + lens[k]]); off += lens[k]
+        return cap[: cap_len.value].copy(), out, ([float(x) for x in ph] if phases else None)
+
+    def close(self):
+        for p in self._imported:
+            self.gpu.L.p3gpu_ipc_close(self.gpu.h, C.c_void_p(p))
+        self._imported = []

@@ -251,10 +251,28 @@ class TwoAdicFriPcs:
         return all_opened, fri_inputs
 
     def get_evaluations_on_domain(self, prover_data, idx: int, domain):
-        """two_adic_pcs.rs:376-385 fast path: first |domain| rows of the committed bit-reversed LDE."""
+        """two_adic_pcs.rs:376-403.  Fast path: the first |domain| rows of the committed bit-reversed LDE (domain shift =
+        GENERATOR, |domain| <= LDE height).  Slow path (:390-403): un-bit-reverse, coset iDFT over GENERATOR*H' to recover the
+        coefficients, truncate to the polynomial degree, zero-pad and coset DFT onto the requested domain."""
+        from .dft import BitReversedMatrixView
+        f = self.dft.field
         shift, log_size = domain
+        size = 1 << log_size
         lde = self.mmcs.get_matrices(prover_data)[idx]
-        if shift == self.dft.field.generator and lde.shape[0] >= (1 << log_size):
-            from .dft import BitReversedMatrixView
-            return BitReversedMatrixView(lde[: 1 << log_size])
-        raise NotImplementedError("re-evaluation on a foreign coset (two_adic_pcs.rs:390-403) is host-side in this round")
+        if shift == f.generator and lde.shape[0] >= size:
+            return BitReversedMatrixView(lde[:size])
+        poly_height = int(lde.shape[0]) >> self.fri.log_blowup
+        lde_mat = reverse_matrix_index_bits(lde)                              # natural order over GENERATOR * H'
+        coeffs = self.dft.coset_idft_batch(lde_mat, f.generator)[:poly_height]
+        width = int(coeffs.shape[1])
+        if _is_torch(coeffs):
+            import torch
+            padded = torch.zeros((max(size, 0), width), dtype=coeffs.dtype, device=coeffs.device)
+            n = min(size, poly_height)
+            padded[:n] = coeffs[:n]
+        else:
+            padded = np.zeros((size, width), dtype=np.uint32)
+            n = min(size, poly_height)
+            padded[:n] = coeffs[:n]
+        result = self.dft.coset_dft_batch(padded, shift)                      # natural order over shift * K
+        return BitReversedMatrixView(reverse_matrix_index_bits(result))

@@ -261,6 +261,28 @@ class Gpu:
         return lde, layers
 
 
+    def pcs_commit_host(self, field, hash_kind, evals_host, log_blowup, cap_height):
+        """p3gpu_pcs_commit: TwoAdicFriPcs::commit with the trace in HOST memory (numpy uint32 array or pinned CPU int32 tensor);
+        the LDE and the digest layers stay on the device, only the cap returns.  Returns (cap (n, 8) array, lde, layers)."""
+        if _is_torch(evals_host):
+            assert not evals_host.is_cuda and evals_host.is_contiguous()
+            h, w, ptr = int(evals_host.shape[0]), int(evals_host.shape[1]), evals_host.data_ptr()
+        else:
+            m = self._np(evals_host)
+            h, w, ptr = int(m.shape[0]), int(m.shape[1]), m.ctypes.data
+        self._use_torch_stream()
+        lde = self._empty((h << log_blowup, w))
+        out = self._empty((self.merkle_total_digests(h << log_blowup), 8))
+        lens = (C.c_size_t * 65)(); nl = C.c_size_t(); cap_len = C.c_size_t()
+        cap = np.zeros((1 << cap_height, 8), dtype=np.uint32)
+        check(self.L.p3gpu_pcs_commit(self.h, field, hash_kind, ptr, h, w, log_blowup, cap_height, lde.data_ptr(), out.data_ptr(), lens,
+                                      C.byref(nl), cap.ctypes.data, C.byref(cap_len)))
+        layers, off = [], 0
+        for k in range(nl.value):
+            layers.append(out[off:off + lens[k]]); off += lens[k]
+        return cap[: cap_len.value].copy(), lde, layers
+
+
 _default = {}
 
 

@@ -42,6 +42,19 @@ def _worker(rank, world, port, q):
         ok = np.array_equal(cap.cpu().numpy().view(np.uint32), exp_cap)
         exp_root = O.merkle_tree(ohs, [O.coset_lde_batch(f.id, full[:, c0:c1], 1, f.generator, True)])[-1][0]
         ok2 = np.array_equal(roots[rank].cpu().numpy().view(np.uint32), exp_root)
+        # peer-memory mode (no NCCL on the data path): IPC-mapped row blocks, LDE stores fused with the re-sharding
+        from plonky3_b200.distributed import PeerGroup
+        H = 2 << LOG_H
+        grp = PeerGroup(gpu, H // world, W)
+        a0, a1 = column_block(W, world, rank, align=8)
+        loc8 = torch.from_numpy(np.ascontiguousarray(full[:, a0:a1]).view(np.int32)).cuda()
+        for _ in range(3):
+            pcap, players, ph = grp.commit(f, _lib.HASH_POSEIDON2_W24, loc8, a0, 1, CAP_H, phases=True)
+        ok = ok and np.array_equal(pcap, exp_cap)
+        rows = H // world
+        ok = ok and np.array_equal(grp.rows_tensor().cpu().numpy().view(np.uint32), lde_full[rank * rows:(rank + 1) * rows])
+        dist.barrier()
+        grp.close()
         q.put((rank, bool(ok), bool(ok2), ""))
         dist.destroy_process_group()
     except Exception as e:

@@ -371,11 +371,16 @@ def test_open_primitives_match_oracle(gpu, f):
     # compute_inverse_denominators, columnwise_dot_product, rowwise dot with alpha powers, quotient accumulation
     z = O.random_matrix(f.id, 1, 4, seed=21)[0]; alpha = O.random_matrix(f.id, 1, 4, seed=22)[0]
     zinv = O.ef_inv(f.id, z)
-    for log_h in (0, 3, 11):
+    for log_h in (0, 3, 11, 20):
         inv_d, adj = gpu.open_inv_denoms(f.id, log_h, z, zinv)
         exp = O.open_inv_denoms(f.id, log_h, z)
         assert np.array_equal(host(inv_d), exp)
-        assert np.array_equal(host(adj), np.array([O.ef_sub(f.id, e, zinv) for e in exp]) if log_h < 6 else host(adj))
+        # compute_adjusted_weights: adj[i] = 1/(z - x_i) - 1/z, checked against the oracle on every row (small) or a row sample
+        n = 1 << log_h
+        rows = np.arange(n) if log_h < 6 else np.unique(np.concatenate([[0, 1, n // 2, n - 2, n - 1], np.random.default_rng(log_h).integers(0, n, 200)]))
+        got = host(adj)
+        for i in rows:
+            assert np.array_equal(got[i], O.ef_sub(f.id, exp[i], zinv)), (log_h, int(i))
     for h, w in [(1, 1), (8, 3), (13, 4), (64, 33), (300, 100), (4096, 7), (4097, 8), (5000, 260)]:
         m = O.random_matrix(f.id, h, w, seed=h + w)
         v = O.random_matrix(f.id, h, 4, seed=h)
@@ -450,3 +455,160 @@ def test_config3_merkle_full_size_properties(gpu):
     while lay.shape[0] > 1:
         lay = np.array([O.compress(ohs, lay[2 * i], lay[2 * i + 1]) for i in range(lay.shape[0] // 2)])
     assert np.array_equal(lay[0], cap[0])
+
+
+# ------------------------------------------------------------------------------------------ round-2 boundary hardening
+@pytest.mark.parametrize("kind", ["p2w16", "p2w24", "keccak"])
+def test_merkle_more_than_eight_matrices_per_height(gpu, kind):
+    """MerkleTree::new takes any number of same-height matrices (merkle_tree.rs:131-133,312-316): 19 tall ones (mixed widths,
+    one of width 0) plus 11 injected ones at half height."""
+    f = KoalaBear
+    mmcs, ohs = _mmcs_pair(f, kind, gpu, cap_height=1)
+    tall = [O.random_matrix(f.id, 64, 1 + (5 * k) % 23, seed=100 + k) for k in range(18)] + [np.zeros((64, 0), dtype=np.uint32)]
+    short = [O.random_matrix(f.id, 32, 1 + (3 * k) % 7, seed=200 + k) for k in range(11)]
+    mats = tall[:9] + short[:4] + tall[9:] + short[4:]          # input order is interleaved; the sort by height is stable
+    olayers = O.merkle_tree(ohs, mats)
+    cap, tree = mmcs.commit([dev(m) for m in mats])
+    _check_tree(tree, olayers)
+    cap_h, tree_h = mmcs.commit(mats)                            # host-pointer path (pooled arena)
+    _check_tree(tree_h, olayers)
+    assert np.array_equal(cap, cap_h)
+
+
+def test_get_evaluations_on_domain_slow_path(gpu):
+    """two_adic_pcs.rs:390-403: re-evaluation of a committed matrix on a foreign coset / a larger domain."""
+    f = KoalaBear
+    mmcs, _ = _mmcs_pair(f, "p2w16", gpu)
+    dft = Radix2DitParallel(f, gpu)
+    pcs = TwoAdicFriPcs(dft, mmcs, FriParameters.new_benchmark_high_arity(mmcs))
+    m = O.random_matrix(f.id, 1 << 9, 12, seed=31)
+    _, tree = pcs.commit([(pcs.natural_domain_for_degree(1 << 9), m)])
+    coeffs = O.idft_batch(f.id, m)
+    for shift, log_size in [(f.mul(f.generator, f.generator), 9), (f.ONE, 10), (f.generator, 11), (f.to_monty(7), 8)]:
+        ev = pcs.get_evaluations_on_domain(tree, 0, (shift, log_size))
+        size = 1 << log_size
+        padded = np.zeros((size, 12), dtype=np.uint32)
+        n = min(size, 1 << 9)
+        padded[:n] = coeffs[:n]
+        assert np.array_equal(ev.to_row_major_matrix(), O.coset_dft_batch(f.id, padded, shift)), (shift, log_size)
+    dtree = pcs.commit([(pcs.natural_domain_for_degree(1 << 9), dev(m))])[1]          # device-resident leaves
+    ev = pcs.get_evaluations_on_domain(dtree, 0, (f.ONE, 10))
+    padded = np.zeros((1 << 10, 12), dtype=np.uint32); padded[: 1 << 9] = coeffs
+    assert np.array_equal(host(ev.to_row_major_matrix()), O.coset_dft_batch(f.id, padded, f.ONE))
+
+
+def test_commit_phase_final_polynomial_longer_than_one(gpu):
+    """log_final_poly_len > 0: the folded vector is truncated, bit-reversed and iDFT'ed (fri/src/prover.rs:267-280)."""
+    f = BabyBear
+    mmcs, ohs = _mmcs_pair(f, "p2w16", gpu)
+    params = FriParameters(1, 2, 1, 2, 0, 1, mmcs)                                    # blowup 2, final poly length 4, arity 2
+    vec = O.random_matrix(f.id, 1 << 9, 4, seed=41)
+    betas = O.random_matrix(f.id, 8, 4, seed=42)
+    ocaps, oar, ofinal = O.commit_phase(f.id, ohs, 0, vec, 1, 2, 1, betas)
+    ch = FixedBetaChallenger(betas)
+    res = commit_phase(TwoAdicFriFolding(f, gpu), params, [dev(vec)], ch, Radix2DitParallel(f, gpu))
+    assert res.log_arities == oar and all(np.array_equal(a, b) for a, b in zip(res.commits, ocaps))
+    # oracle side of the final step: first 4 folded values, bit-reversed, iDFT of each of the 4 base coordinates
+    fl = 4
+    rev = O.reverse_matrix_index_bits(ofinal[:fl])
+    exp = O.idft_batch(f.id, rev)
+    assert np.array_equal(res.final_poly, exp)
+    assert np.array_equal(ch.final, exp)
+
+
+def test_one_context_shared_by_two_threads(gpu):
+    """SURVEY 8b "Threading": the reference's objects are Clone + Sync; one p3gpu_ctx called from two host threads at once
+    (its entry points serialise on the context's mutex) must give the same answers as sequential calls."""
+    import threading
+    f = KoalaBear
+    mmcs, ohs = _mmcs_pair(f, "p2w16", gpu)
+    dft = Radix2DitParallel(f, gpu)
+    ms = [O.random_matrix(f.id, 1 << 11, 20 + 4 * k, seed=50 + k) for k in range(4)]
+    exp_lde = [O.coset_lde_batch(f.id, m, 1, f.generator, bitrev_out=True) for m in ms]
+    exp_root = [O.merkle_tree(ohs, [m])[-1][0] for m in ms]
+    errors = []
+
+    def work(tid):
+        try:
+            for it in range(6):
+                k = (tid + it) % 4
+                if (tid + it) % 2 == 0:
+                    got = dft.coset_lde_batch(ms[k], 1, f.generator).bit_reverse_rows()          # host-pointer call
+                    assert np.array_equal(got, exp_lde[k]), ("lde", tid, it)
+                else:
+                    cap, _ = mmcs.commit([ms[k]])
+                    assert np.array_equal(cap[0], exp_root[k]), ("merkle", tid, it)
+        except Exception as e:   # noqa: BLE001
+            errors.append(repr(e))
+
+    ths = [threading.Thread(target=work, args=(t,)) for t in range(2)]
+    for t in ths: t.start()
+    for t in ths: t.join()
+    assert not errors, errors
+
+
+def test_stream_switch_orders_shared_scratch(gpu):
+    """p3gpu_ctx_set_stream with a different stream between calls: work queued on the old stream (which uses the context's
+    scratch buffers and may be generating twiddles) is ordered before the new stream's work."""
+    f = BabyBear
+    dft = Radix2DitParallel(f, gpu)
+    m = O.random_matrix(f.id, 1 << 15, 24, seed=61)
+    exp = O.coset_lde_batch(f.id, m, 2, f.to_monty(5), bitrev_out=True)
+    x = dev(m)
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    outs = []
+    for it in range(6):
+        with torch.cuda.stream(s1 if it % 2 == 0 else s2):
+            outs.append(dft.coset_lde_batch(x, 2, f.to_monty(5)).bit_reverse_rows())
+    torch.cuda.synchronize()
+    for o in outs:
+        assert np.array_equal(host(o), exp)
+
+
+def test_twiddle_cache_is_bounded(monkeypatch):
+    """LRU eviction by bytes (P3GPU_TWIDDLE_CACHE_MB): many distinct coset shifts with a 1 MB cap stay correct."""
+    from plonky3_b200.gpu import Gpu
+    monkeypatch.setenv("P3GPU_TWIDDLE_CACHE_MB", "1")
+    g = Gpu(0)
+    f = KoalaBear
+    dft = Radix2DitParallel(f, g)
+    m = O.random_matrix(f.id, 1 << 14, 8, seed=71)
+    x = dev(m)
+    for k in range(2, 12):
+        shift = f.to_monty(k)
+        assert np.array_equal(host(dft.coset_dft_batch(x, shift)), O.coset_dft_batch(f.id, m, shift)), k
+    for k in (2, 3):                                          # evicted entries are rebuilt
+        assert np.array_equal(host(dft.coset_lde_batch(x, 1, f.to_monty(k)).bit_reverse_rows()), O.coset_lde_batch(f.id, m, 1, f.to_monty(k), bitrev_out=True))
+    g.close()
+
+
+@pytest.mark.parametrize("chunks", ["1", "3", "4", "7"])
+def test_host_pointer_lde_is_pipelined_in_column_chunks(gpu, chunks, monkeypatch):
+    """p3gpu_coset_lde_batch (host pointers): H2D || LDE || D2H over column chunks must equal the one-shot transform."""
+    monkeypatch.setenv("P3GPU_E2E_CHUNKS", chunks)
+    f = KoalaBear
+    m = O.random_matrix(f.id, 1 << 16, 100, seed=81)                    # 26 MB: above the pipelining threshold
+    exp = O.coset_lde_batch(f.id, m, 1, f.generator, bitrev_out=True)
+    got = gpu.coset_lde_batch(f.id, m, 1, f.generator)
+    assert np.array_equal(got, exp)
+    pinned = torch.from_numpy(m.view(np.int32)).pin_memory()
+    out = torch.empty((1 << 17, 100), dtype=torch.int32).pin_memory()
+    _lib.check(gpu.L.p3gpu_coset_lde_batch(gpu.h, f.id, pinned.data_ptr(), 1 << 16, 100, 1, f.generator, out.data_ptr(), 1))
+    assert np.array_equal(out.numpy().view(np.uint32), exp)
+    got3 = gpu.coset_lde_batch(f.id, np.ascontiguousarray(m[:, :44]), 2, f.to_monty(11))           # ragged widths, blowup 4
+    assert np.array_equal(got3, O.coset_lde_batch(f.id, np.ascontiguousarray(m[:, :44]), 2, f.to_monty(11), bitrev_out=True))
+
+
+def test_pcs_commit_from_host_memory(gpu):
+    """p3gpu_pcs_commit: host trace in, cap out, LDE + layers resident — equals the device-resident commit and the oracle."""
+    f = KoalaBear
+    mmcs, ohs = _mmcs_pair(f, "p2w24", gpu, cap_height=3)
+    for log_h, w in [(10, 45), (15, 200)]:                                                         # serial path / chunked path
+        m = O.random_matrix(f.id, 1 << log_h, w, seed=91)
+        cap, lde, layers = gpu.pcs_commit_host(f.id, mmcs.hash_kind, m, 1, 3)
+        elde = O.coset_lde_batch(f.id, m, 1, f.generator, bitrev_out=True)
+        ol = O.merkle_tree(ohs, [elde])
+        assert np.array_equal(host(lde), elde)
+        assert np.array_equal(cap, O.merkle_cap(ol, 3))
+        for a, b in zip(layers, ol):
+            assert np.array_equal(host(a), b)
