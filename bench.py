@@ -13,8 +13,8 @@ output.  A "step" is one LDE of one synthetic matrix (uniform field elements, se
               all-to-all that re-shards column blocks into row blocks), followed by the flag barrier that makes the
               step complete on all ranks.  value = N x 209,715,200 elements / max-over-ranks time.
   e2e         the same metric through the reference-facing C-ABI call p3gpu_coset_lde_batch with HOST (pinned, NUMA-local)
-              buffers, ONE call at a time: H2D of the input and D2H of the result are inside the timed region (the call
-              pipelines column chunks on three streams internally).  The 2-calls-in-flight figure is reported as a note.
+              buffers, ONE call at a time: H2D of the input and D2H of the result are inside the timed region.  The
+              2-calls-in-flight figure (two contexts, full-duplex PCIe) is reported as a note.
   roofline    HBM roofline of the NTT pass kernel: algorithmic bytes of one LDE (read input once + write output once,
               SURVEY.md 8d: 1,258,291,200 B) / device time of the step (all launches of a step are the same kernel), plus the
               integer-issue floor the kernel is actually bound by.
@@ -366,8 +366,8 @@ def main():
         del ref_out
         line["e2e"] = {"value": world * OUT_ELEMS / (single_ms * 1e-3) / 1e9, "unit": "Gelem/s", "ms_per_step": single_ms,
                        "h2d_bytes_per_step": lanes[0][1].numel() * 4, "d2h_bytes_per_step": lanes[0][2].numel() * 4,
-                       "api": "p3gpu_coset_lde_batch (host pointers, pinned, NUMA-local), ONE call at a time; the call pipelines H2D || LDE || D2H over "
-                              f"{os.environ.get('P3GPU_E2E_CHUNKS', '4')} column chunks on three streams",
+                       "api": "p3gpu_coset_lde_batch (host pointers, pinned, NUMA-local), ONE call at a time (strictly serial H2D -> LDE -> D2H with contiguous copies; "
+                              f"P3GPU_E2E_CHUNKS={os.environ.get('P3GPU_E2E_CHUNKS', '1')}: the chunk-pipelined variant is slower on this PCIe, profiles/r02_pcie_probe.txt)",
                        "two_calls_in_flight_ms": two_ms, "two_calls_in_flight_value": world * OUT_ELEMS / (two_ms * 1e-3) / 1e9,
                        "d2h_floor_ms_at_55GBps": lanes[0][2].numel() * 4 / 55e9 * 1e3,
                        "timer": "host wall clock around the calls (device work is synchronous inside the call), max over ranks"}
@@ -633,6 +633,33 @@ def others(gpu, timed, g, dev, peak, KB, BB, _lib, torch, np):
         "note": "device-resident LDE + Merkle + open + FRI commit phase (per-round transcript round trip) of prove_prime_field_31 -f koala-bear "
                 "-o poseidon-2-permutations -l 20"}
     del v1, xq
+    # config 5 end to end (BASELINE's lead metric): prove_prime_field_31 -f koala-bear -o poseidon-2-permutations -l 20 -d radix-2-dit-parallel
+    # -m poseidon-2 = uni-stark prove of 2^23 Poseidon2 permutations (8 per row), every data-parallel step on the device
+    from plonky3_b200.fri import TwoAdicFriPcs
+    from plonky3_b200.uni_stark import RoundConstants, StarkConfig, VectorizedPoseidon2Air, prove
+    torch.cuda.empty_cache()
+    rs = np.random.default_rng(7)
+    rc = RoundConstants(rs.integers(0, KB.P, (4, 16), dtype=np.uint32), rs.integers(0, KB.P, 20, dtype=np.uint32), rs.integers(0, KB.P, (4, 16), dtype=np.uint32))
+    air = VectorizedPoseidon2Air(KB, rc, gpu)
+    cfg = StarkConfig(TwoAdicFriPcs(Radix2DitParallel(KB, gpu), mm5, p5), default_poseidon2(KB, 24), 16)
+    perm_inputs = torch.randint(0, KB.P, (1 << 23, 16), device=dev, dtype=torch.int32, generator=g)
+    t_gen, _ = timed(lambda: air.generate_trace_rows(perm_inputs), 2, 1)
+    trace = air.generate_trace_rows(perm_inputs)
+    del perm_inputs
+    prove(cfg, air, trace)                                   # warm-up (twiddles, allocator)
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    reps = 2
+    for _ in range(reps):
+        proof = prove(cfg, air, trace)
+    torch.cuda.synchronize()
+    t_prove = (time.perf_counter() - t0) * 1e3 / reps
+    o["config5_prove_kb_2^20x1312"] = {
+        "prove_ms": t_prove, "trace_generation_ms": t_gen, "spans_ms": proof.timings_ms, "permutations_proved": 1 << 23,
+        "fri": {"log_blowup": 1, "max_log_arity": 3, "num_queries": 100, "query_pow_bits": 16, "cap_height": 3},
+        "timer": "host wall clock around prove() with the trace resident on the device (synchronised before and after)",
+        "note": "uni-stark prove (uni-stark/src/prover.rs:87-442) with trace commit, quotient, quotient commit, opening, FRI commit phase, "
+                "proof-of-work and the 100 query openings all on the device; the transcript sponge is device resident (csrc/challenger.cu)"}
+    del trace, proof
     return o
 
 

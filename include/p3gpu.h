@@ -38,6 +38,7 @@ extern "C" {
 #endif
 
 typedef struct p3gpu_ctx p3gpu_ctx;
+typedef struct p3gpu_challenger p3gpu_challenger;
 
 enum { P3GPU_BABY_BEAR = 0, P3GPU_KOALA_BEAR = 1 };
 
@@ -102,9 +103,10 @@ int32_t p3gpu_dft_batch(p3gpu_ctx *ctx, int field, int kind, uint32_t *h_inout, 
  * d_out must not alias d_in. */
 int32_t p3gpu_coset_lde_batch_dev(p3gpu_ctx *ctx, int field, const uint32_t *d_in, size_t h, size_t w,
                                   unsigned added_bits, uint32_t shift, uint32_t *d_out, int bitrev_rows);
-/* Host-pointer variant: large calls are pipelined internally in column chunks on three streams — H2D(chunk i+1) || LDE(chunk i)
- * || D2H(chunk i-1) — so ONE call approaches the PCIe floor max(H2D, D2H) (P3GPU_E2E_CHUNKS, default 4; page-lock the buffers
- * with p3gpu_host_register for full rate). */
+/* Host-pointer variant (page-lock the buffers with p3gpu_host_register for full PCIe rate).  With P3GPU_E2E_CHUNKS = n > 1 the call
+ * is pipelined internally in n column chunks on three streams — H2D(chunk i+1) || LDE(chunk i) || D2H(chunk i-1); the default is
+ * 1 (strictly serial, contiguous copies) because 2-D copies of narrow chunks run at 60-75 % of the contiguous PCIe rate on the
+ * measured hosts (profiles/r02_pcie_probe.txt), which cancels the overlap for matrices of a few hundred bytes per row. */
 int32_t p3gpu_coset_lde_batch(p3gpu_ctx *ctx, int field, const uint32_t *h_in, size_t h, size_t w,
                               unsigned added_bits, uint32_t shift, uint32_t *h_out, int bitrev_rows);
 
@@ -200,6 +202,45 @@ int32_t p3gpu_pcs_commit_dev(p3gpu_ctx *ctx, int field, int hash, const uint32_t
 int32_t p3gpu_pcs_commit(p3gpu_ctx *ctx, int field, int hash, const uint32_t *h_evals, size_t h, size_t w, unsigned log_blowup,
                          unsigned cap_height, uint32_t *d_lde, uint32_t *d_layers, size_t *layer_lens, size_t *n_layers,
                          uint32_t *h_cap, size_t *cap_len);
+
+/* ---- Poseidon2 AIR: the AIR of prove_prime_field_31 -o poseidon-2-permutations ---------------
+ * VectorizedPoseidon2Air<KoalaBear, width 16, S-box degree 3, 0 S-box registers, 4 + rounds_p + 4 rounds> (poseidon2-air/src/
+ * air.rs, vectorized.rs).  Only the KoalaBear instance is built (BabyBear's degree-7 S-box needs register columns).
+ * RoundConstants::new (poseidon2-air/src/constants.rs:47-57): 4 x 16 beginning, rounds_p partial, 4 x 16 ending, Montgomery. */
+int32_t p3gpu_p2air_set_constants(p3gpu_ctx *ctx, int field, const uint32_t *beginning_full, const uint32_t *partial, int rounds_p,
+                                  const uint32_t *ending_full);
+/* columns of ONE permutation: 16 inputs + 4*16 + rounds_p + 4*16 (columns.rs:11-48) */
+size_t p3gpu_p2air_columns(int rounds_p);
+/* generate_vectorized_trace_rows (poseidon2-air/src/generation.rs:14-70): d_inputs n_perms x 16 -> d_trace n_perms x columns,
+ * i.e. the (n_perms / VECTOR_LEN) x (VECTOR_LEN * columns) row-major trace. */
+int32_t p3gpu_p2air_generate_trace_dev(p3gpu_ctx *ctx, int field, const uint32_t *d_inputs, size_t n_perms, uint32_t *d_trace);
+/* quotient_values (uni-stark/src/prover.rs:462-827) of that AIR over the quotient domain GENERATOR * K with |K| = the LDE height
+ * (log_quotient_degree == log_blowup: the truncation fast path of get_evaluations_on_domain, two_adic_pcs.rs:376-385).
+ * d_lde: the committed trace LDE, 2^log_lde_height rows in bit-reversed order, vector_len * columns wide.
+ * d_quotient: 2^log_lde_height EF4 values in NATURAL order (what commit_quotient / split_evals consume). */
+int32_t p3gpu_p2air_quotient_dev(p3gpu_ctx *ctx, int field, int vector_len, const uint32_t *d_lde, unsigned log_lde_height,
+                                 unsigned log_trace_height, const uint32_t alpha[4], uint32_t *d_quotient);
+
+/* ---- transcript and query phase of the prove driver ----------------------------------------
+ * DuplexChallenger<F, Poseidon2<width>, width, rate> (challenger/src/duplex_challenger.rs:60-300) with its state resident on the
+ * device, so that caps and opened values produced on the GPU are absorbed without a PCIe round trip per duplexing.  The
+ * Poseidon2 constants of (field, width) must have been set.  Values are Montgomery words; `observe` of an EF4 element = its 4
+ * coefficients in order; sampled elements pop from the END of the rate (duplex_challenger.rs:255-268). */
+int32_t p3gpu_challenger_new(p3gpu_ctx *ctx, int field, int width, int rate, p3gpu_challenger **out);
+void p3gpu_challenger_free(p3gpu_ctx *ctx, p3gpu_challenger *ch);
+int32_t p3gpu_challenger_clone(p3gpu_ctx *ctx, const p3gpu_challenger *src, p3gpu_challenger **out);
+int32_t p3gpu_challenger_observe_dev(p3gpu_ctx *ctx, p3gpu_challenger *ch, const uint32_t *d_values, size_t n);
+int32_t p3gpu_challenger_observe(p3gpu_ctx *ctx, p3gpu_challenger *ch, const uint32_t *h_values, size_t n);
+int32_t p3gpu_challenger_sample(p3gpu_ctx *ctx, p3gpu_challenger *ch, uint32_t *h_out, size_t n);   /* synchronous */
+/* GrindingChallenger::grind (grinding_challenger.rs:100-232): parallel search on the device, returns the SMALLEST witness (what a
+ * serial reference build returns), observes it and consumes the checked sample. */
+int32_t p3gpu_challenger_grind(p3gpu_ctx *ctx, p3gpu_challenger *ch, unsigned bits, uint32_t *witness);
+/* Mmcs::open_batch for n indices at once (merkle-tree/src/mmcs/batch.rs:75-121): d_out[q] = row (h_indices[q] >> index_shift) of a
+ * device matrix; and the authentication paths: d_out[q][l] = sibling digest at layer l, l < path_len = layers - 1 - cap_height. */
+int32_t p3gpu_gather_rows_dev(p3gpu_ctx *ctx, const uint32_t *d_mat, size_t h, size_t w, const uint32_t *h_indices, size_t n, unsigned index_shift,
+                              uint32_t *d_out);
+int32_t p3gpu_merkle_paths_dev(p3gpu_ctx *ctx, const uint32_t *d_layers, const size_t *layer_lens, size_t n_layers, size_t path_len,
+                               const uint32_t *h_indices, size_t n, unsigned index_shift, uint32_t *d_out);
 
 /* ---- multi-GPU: one process per GPU, peer memory over NVLink ------------------
  * The path shards by COLUMN for the LDE (every column is an independent polynomial, dft/src/traits.rs:22-24) and by

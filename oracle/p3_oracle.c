@@ -689,3 +689,164 @@ void p3o_open_reduce(int fi, u32 *ro, const u32 *r, const u32 *inv_denoms, size_
         for (int k = 0; k < 4; k++) ro[4 * i + k] = f_add(f, ro[4 * i + k], t[k]);
     }
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * Poseidon2 AIR: VectorizedPoseidon2Air with WIDTH 16, S-box degree 3 and 0 S-box registers
+ * (the KoalaBear instance of prove_prime_field_31, examples/examples/prove_prime_field_31.rs:150-165).
+ *   columns of one permutation (poseidon2-air/src/columns.rs:11-48):
+ *     inputs[16] | 4 x post[16] (beginning full rounds) | rounds_p x post_sbox | 4 x post[16] (ending full rounds)
+ *   trace generation: poseidon2-air/src/generation.rs:184-253 (+ full/partial round :430-553)
+ *   constraints:      poseidon2-air/src/air.rs:173-240 (eval), :254-275 (full round), :277-296 (partial round),
+ *                     vectorised: poseidon2-air/src/vectorized.rs:297-311 (VECTOR_LEN permutations per row, in order)
+ *   folding:          uni-stark/src/folder.rs (first asserted constraint gets the highest power of alpha),
+ *                     quotient = folded * inv_vanishing, uni-stark/src/prover.rs:462-827, commit/src/domain.rs:321-361
+ * The linear layers are the permutation's own (GenericPoseidon2LinearLayersMonty31 == the optimised layers,
+ * koala-bear/src/poseidon2.rs:575-610).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+    int field;          /* 1 = KoalaBear (degree-3 S-box, no registers); other instances are not restated */
+    int rounds_p;       /* partial rounds (20 for KoalaBear width 16) */
+    u32 beg[4 * 16];    /* beginning_full_round_constants, Montgomery */
+    u32 part[32];       /* partial_round_constants */
+    u32 end[4 * 16];    /* ending_full_round_constants */
+} p3o_air;
+
+size_t p3o_p2air_cols(const p3o_air *a) { return 16 + 64 + (size_t)a->rounds_p + 64; }
+size_t p3o_p2air_constraints(const p3o_air *a) { return 64 + (size_t)a->rounds_p + 64; }
+
+static void air_internal_layer(const field_t *f, const u32 *diag, u32 *s) {
+    u32 sum = 0;
+    for (int i = 0; i < 16; i++) sum = f_add(f, sum, s[i]);
+    for (int i = 0; i < 16; i++) s[i] = f_add(f, f_mul(f, s[i], diag[i]), sum);
+}
+
+/* generate_trace_rows_for_perm for n_perms inputs; row-major n_perms x cols (the vectorised trace is the same buffer viewed as
+ * (n_perms / VECTOR_LEN) x (VECTOR_LEN * cols), generation.rs:14-70) */
+void p3o_p2air_generate(const p3o_air *a, const u32 *inputs, size_t n_perms, u32 *trace) {
+    const field_t *f = F(a->field);
+    const size_t cols = p3o_p2air_cols(a);
+    u32 diag[P2_MAXW];
+    p3o_poseidon2_diag(a->field, 16, diag);
+    #pragma omp parallel for schedule(static)
+    for (size_t p = 0; p < n_perms; p++) {
+        u32 s[16];
+        u32 *row = trace + p * cols;
+        memcpy(s, inputs + p * 16, 64);
+        memcpy(row, s, 64);
+        row += 16;
+        mds_light(f, s, 16);
+        for (int r = 0; r < 4; r++) {
+            for (int i = 0; i < 16; i++) s[i] = sbox(f, f_add(f, s[i], a->beg[r * 16 + i]));
+            mds_light(f, s, 16);
+            memcpy(row, s, 64); row += 16;
+        }
+        for (int r = 0; r < a->rounds_p; r++) {
+            s[0] = sbox(f, f_add(f, s[0], a->part[r]));
+            *row++ = s[0];
+            air_internal_layer(f, diag, s);
+        }
+        for (int r = 0; r < 4; r++) {
+            for (int i = 0; i < 16; i++) s[i] = sbox(f, f_add(f, s[i], a->end[r * 16 + i]));
+            mds_light(f, s, 16);
+            memcpy(row, s, 64); row += 16;
+        }
+    }
+}
+
+/* the constraints of ONE permutation on one row of column values (any field point of the LDE): out[k], k < constraints */
+static void air_eval_perm(const p3o_air *a, const field_t *f, const u32 *diag, const u32 *c, u32 *out) {
+    u32 s[16];
+    memcpy(s, c, 64); c += 16;
+    mds_light(f, s, 16);
+    for (int r = 0; r < 4; r++) {
+        for (int i = 0; i < 16; i++) s[i] = sbox(f, f_add(f, s[i], a->beg[r * 16 + i]));
+        mds_light(f, s, 16);
+        for (int i = 0; i < 16; i++) { *out++ = f_sub(f, s[i], c[i]); s[i] = c[i]; }     /* assert_eq(state_i, post_i); state_i = post_i */
+        c += 16;
+    }
+    for (int r = 0; r < a->rounds_p; r++) {
+        const u32 x = sbox(f, f_add(f, s[0], a->part[r]));
+        *out++ = f_sub(f, x, *c);                                                           /* assert_eq(state_0, post_sbox) */
+        s[0] = *c++;
+        air_internal_layer(f, diag, s);
+    }
+    for (int r = 0; r < 4; r++) {
+        for (int i = 0; i < 16; i++) s[i] = sbox(f, f_add(f, s[i], a->end[r * 16 + i]));
+        mds_light(f, s, 16);
+        for (int i = 0; i < 16; i++) { *out++ = f_sub(f, s[i], c[i]); s[i] = c[i]; }
+        c += 16;
+    }
+}
+
+/* check_constraints-style helper for tests: number of non-zero constraints over a (vectorised) trace */
+size_t p3o_p2air_check(const p3o_air *a, int vec_len, const u32 *trace, size_t rows) {
+    const field_t *f = F(a->field);
+    const size_t cols = p3o_p2air_cols(a), nc = p3o_p2air_constraints(a);
+    u32 diag[P2_MAXW];
+    p3o_poseidon2_diag(a->field, 16, diag);
+    size_t bad = 0;
+    for (size_t r = 0; r < rows; r++)
+        for (int v = 0; v < vec_len; v++) {
+            u32 out[64 + 32 + 64];
+            air_eval_perm(a, f, diag, trace + (r * vec_len + v) * cols, out);
+            for (size_t k = 0; k < nc; k++) bad += out[k] != 0;
+        }
+    return bad;
+}
+
+/* quotient_values (uni-stark/src/prover.rs:462-827) for this AIR.  lde: the committed trace LDE, H = 2^log_h rows in
+ * BIT-REVERSED order (row m = evaluation at GENERATOR * w_H^bitrev(m)), width vec_len * cols; log_n: log2 of the trace height.
+ * q: H x 4, NATURAL order over the quotient domain GENERATOR * K, |K| = H (requires quotient degree == blow-up, the fast path of
+ * get_evaluations_on_domain, two_adic_pcs.rs:376-385).  alpha: 4 Montgomery words. */
+void p3o_p2air_quotient(const p3o_air *a, int vec_len, const u32 *lde, unsigned log_h, unsigned log_n, const u32 *alpha, u32 *q) {
+    const field_t *f = F(a->field);
+    const size_t cols = p3o_p2air_cols(a), nc = p3o_p2air_constraints(a), n_all = nc * (size_t)vec_len, H = (size_t)1 << log_h;
+    const unsigned rate_bits = log_h - log_n;
+    u32 diag[P2_MAXW];
+    p3o_poseidon2_diag(a->field, 16, diag);
+    /* alpha powers: constraint j is multiplied by alpha^(n_all - 1 - j)  (Horner, folder.rs:374-376) */
+    u32 *apow = (u32 *)malloc(n_all * 16);
+    apow[0] = f_one(f); apow[1] = apow[2] = apow[3] = 0;
+    for (size_t j = 1; j < n_all; j++) ef_mul(f, apow + 4 * (j - 1), alpha, apow + 4 * j);
+    /* inv_vanishing on the coset (domain.rs:326-360): Z_H(x_i) = s^N * w_(2^rate_bits)^(i mod 2^rate_bits) - 1 */
+    const size_t nz = (size_t)1 << rate_bits;
+    u32 *invz = (u32 *)malloc(nz * 4);
+    const u32 s_pow_n = f_pow(f, f_to_monty(f, f->gen), (u64)1 << log_n), wr = f_two_adic_generator(f, rate_bits);
+    for (size_t k = 0; k < nz; k++) invz[k] = f_inv(f, f_sub(f, f_mul(f, s_pow_n, f_pow(f, wr, k)), f_one(f)));
+    #pragma omp parallel for schedule(static)
+    for (size_t i = 0; i < H; i++) {
+        const u32 *row = lde + bitrev(i, log_h) * (cols * vec_len);
+        u32 acc[4] = {0, 0, 0, 0}, out[64 + 32 + 64];
+        for (int v = 0; v < vec_len; v++) {
+            air_eval_perm(a, f, diag, row + (size_t)v * cols, out);
+            for (size_t k = 0; k < nc; k++) {
+                const u32 *ap = apow + 4 * (n_all - 1 - ((size_t)v * nc + k));
+                for (int d = 0; d < 4; d++) acc[d] = f_add(f, acc[d], f_mul(f, out[k], ap[d]));
+            }
+        }
+        for (int d = 0; d < 4; d++) q[4 * i + d] = f_mul(f, acc[d], invz[i & (nz - 1)]);
+    }
+    free(apow); free(invz);
+}
+
+/* rand 0.10 SmallRng on 64-bit targets (xoshiro256++ seeded through SplitMix64) + the MontyField31 sampler
+ * (monty-31/src/monty_31.rs:154-165: v = next_u32 >> 1, rejected if >= p, value taken AS the Montgomery representation).
+ * Pinned by the fixture replay.  Fills out[n] with consecutive field samples; state (4 x u64) in/out. */
+void p3o_smallrng_seed(u64 seed, u64 *st) {
+    u64 x = seed;
+    for (int i = 0; i < 4; i++) {
+        x += 0x9e3779b97f4a7c15ULL;
+        u64 z = x;
+        z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ULL; z = (z ^ (z >> 27)) * 0x94d049bb133111ebULL;
+        st[i] = z ^ (z >> 31);
+    }
+}
+void p3o_smallrng_field(int fi, u64 *s, u32 *out, size_t n) {
+    const u32 p = F(fi)->p;
+    for (size_t k = 0; k < n;) {
+        const u64 r = rotl64(s[0] + s[3], 23) + s[0], t = s[1] << 17;
+        s[2] ^= s[0]; s[3] ^= s[1]; s[1] ^= s[2]; s[0] ^= s[3]; s[2] ^= t; s[3] = rotl64(s[3], 45);
+        const u32 v = (u32)(r >> 32) >> 1;
+        if (v < p) out[k++] = v;
+    }
+}

@@ -37,6 +37,11 @@ class Perm(C.Structure):
                 ("rc_int", C.c_uint32 * 32)]
 
 
+class Air(C.Structure):
+    """p3o_air: VectorizedPoseidon2Air round constants (width 16, degree-3 S-box: the KoalaBear instance)."""
+    _fields_ = [("field", C.c_int), ("rounds_p", C.c_int), ("beg", C.c_uint32 * 64), ("part", C.c_uint32 * 32), ("end", C.c_uint32 * 64)]
+
+
 class Hasher(C.Structure):
     _fields_ = [("kind", C.c_int), ("leaf_rate", C.c_int), ("leaf", Perm), ("comp", Perm)]
 
@@ -77,6 +82,11 @@ def lib():
             ("p3o_columnwise_dot", None, [C.c_int, C.c_void_p, sz, sz, C.c_void_p, C.c_void_p]),
             ("p3o_rowwise_dot", None, [C.c_int, C.c_void_p, sz, sz, C.c_void_p, C.c_void_p]),
             ("p3o_open_reduce", None, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, sz, C.c_void_p, C.c_void_p]),
+            ("p3o_p2air_cols", sz, [C.POINTER(Air)]), ("p3o_p2air_constraints", sz, [C.POINTER(Air)]),
+            ("p3o_p2air_generate", None, [C.POINTER(Air), C.c_void_p, sz, C.c_void_p]),
+            ("p3o_p2air_check", sz, [C.POINTER(Air), C.c_int, C.c_void_p, sz]),
+            ("p3o_p2air_quotient", None, [C.POINTER(Air), C.c_int, C.c_void_p, C.c_uint, C.c_uint, C.c_void_p, C.c_void_p]),
+            ("p3o_smallrng_seed", None, [u64, C.c_void_p]), ("p3o_smallrng_field", None, [C.c_int, C.c_void_p, C.c_void_p, sz]),
         ]:
             fn = getattr(L, name)
             fn.restype, fn.argtypes = res, args
@@ -387,3 +397,69 @@ def commit_phase(f, hs: Hasher, cap_height, inputs, log_blowup, log_final_poly_l
                 t = ef_mul(f, bp, x[i])
                 folded[i] = [add(f, int(a), int(b)) for a, b in zip(folded[i], t)]
     return caps, arities, folded
+
+
+# ---------------------------------------------------------------- Poseidon2 AIR + SmallRng
+class SmallRng:
+    """rand 0.10 SmallRng (xoshiro256++ via SplitMix64) drawing MontyField31 samples (values ARE Montgomery representations)."""
+
+    def __init__(self, seed: int):
+        self.state = np.zeros(4, dtype=np.uint64)
+        lib().p3o_smallrng_seed(seed, _ptr(self.state))
+
+    def field(self, f, n):
+        out = np.empty(int(n), dtype=np.uint32)
+        lib().p3o_smallrng_field(f, _ptr(self.state), _ptr(out), int(n))
+        return out
+
+
+def make_air(f, beg, part, end) -> Air:
+    """RoundConstants::new (poseidon2-air/src/constants.rs:47-57); constants in Montgomery form."""
+    a = Air()
+    a.field = f
+    part = _u32(part).ravel()
+    a.rounds_p = part.size
+    for i, v in enumerate(_u32(beg).ravel()): a.beg[i] = int(v)
+    for i, v in enumerate(part): a.part[i] = int(v)
+    for i, v in enumerate(_u32(end).ravel()): a.end[i] = int(v)
+    return a
+
+
+def air_from_rng(f, rng: SmallRng, rounds_p=20) -> Air:
+    """RoundConstants::from_rng (constants.rs:59-68): beginning full rounds, partial rounds, ending full rounds, in that order."""
+    beg = rng.field(f, 64); part = rng.field(f, rounds_p); end = rng.field(f, 64)
+    return make_air(f, beg, part, end)
+
+
+def perm_from_rng(f, width, rng: SmallRng) -> Perm:
+    """Poseidon2::new_from_rng_128 (poseidon2/src/lib.rs:92-107): 4 x width initial, 4 x width terminal, then R_P internal."""
+    rp = {(0, 16): 13, (0, 24): 21, (1, 16): 20, (1, 24): 23}[(f, width)]
+    init = rng.field(f, 4 * width); term = rng.field(f, 4 * width); internal = rng.field(f, rp)
+    return make_perm(f, width, init, term, internal, monty=True)
+
+
+def p2air_cols(a: Air): return int(lib().p3o_p2air_cols(C.byref(a)))
+def p2air_constraints(a: Air): return int(lib().p3o_p2air_constraints(C.byref(a)))
+
+
+def p2air_generate(a: Air, inputs, vec_len=8):
+    """generate_vectorized_trace_rows (generation.rs:14-70): inputs (n_perms, 16) -> trace (n_perms / vec_len, vec_len * cols)."""
+    x = _u32(inputs); n = x.shape[0]
+    cols = p2air_cols(a)
+    out = np.empty((n, cols), dtype=np.uint32)
+    lib().p3o_p2air_generate(C.byref(a), _ptr(x), n, _ptr(out))
+    return out.reshape(n // vec_len, vec_len * cols)
+
+
+def p2air_check(a: Air, trace, vec_len=8):
+    t = _u32(trace)
+    return int(lib().p3o_p2air_check(C.byref(a), vec_len, _ptr(t), t.shape[0]))
+
+
+def p2air_quotient(a: Air, lde_bitrev, log_n, alpha, vec_len=8):
+    """quotient_values over the quotient domain GENERATOR * K, |K| = LDE height; natural order, (H, 4)."""
+    m = _u32(lde_bitrev); al = _u32(alpha)
+    log_h = int(np.log2(m.shape[0]))
+    q = np.empty((m.shape[0], 4), dtype=np.uint32)
+    lib().p3o_p2air_quotient(C.byref(a), vec_len, _ptr(m), log_h, log_n, _ptr(al), _ptr(q))
+    return q

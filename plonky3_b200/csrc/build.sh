@@ -8,10 +8,10 @@ NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -ccbin /usr/bin/g++ $*"
 mkdir -p $OBJ
 pids=()
-for f in ntt hash fri open peer capi; do
+for f in ntt hash fri open peer air challenger query capi; do
   $NVCC $FLAGS -c $f.cu -o $OBJ/$f.o &
   pids+=($!)
 done
 for p in "${pids[@]}"; do wait $p; done
-$NVCC -gencode arch=compute_100a,code=sm_100a -shared -ccbin /usr/bin/g++ -o $OUT $OBJ/{ntt,hash,fri,open,peer,capi}.o
+$NVCC -gencode arch=compute_100a,code=sm_100a -shared -ccbin /usr/bin/g++ -o $OUT $OBJ/{ntt,hash,fri,open,peer,air,challenger,query,capi}.o
 echo "built $(realpath $OUT)"

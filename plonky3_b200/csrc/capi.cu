@@ -224,10 +224,14 @@ static std::vector<size_t> column_chunks(size_t w, size_t n_chunks) {
     for (size_t c = 1; c <= n_chunks; c++) b.push_back(c == n_chunks ? w : w - (units * (n_chunks - c) / n_chunks) * 8);
     return b;
 }
-static size_t host_chunk_count(size_t bytes_in) {
+// Chunks of the round-trip pipeline (p3gpu_coset_lde_batch).  Default 1 = strictly serial contiguous copies: measured on the
+// bench host (profiles/r02_pcie_probe.txt) the copy engines move 2-D chunks of a 400-byte-pitch matrix at 31-41 GB/s (96-192 byte
+// row segments) against 51-55 GB/s for contiguous copies, which eats the overlap (4 chunks: 31.8 ms, 1 chunk: 24.4 ms for the
+// 2^20 x 100 LDE).  Wide matrices (>= 512-byte row segments per chunk) do profit: set P3GPU_E2E_CHUNKS.
+static size_t host_chunk_count(size_t bytes_in, size_t dflt) {
     if (bytes_in < ((size_t)16 << 20)) return 1;          // small calls: latency, not bandwidth
     const char *e = getenv("P3GPU_E2E_CHUNKS");
-    const long v = e ? atol(e) : 4;
+    const long v = e ? atol(e) : (long)dflt;
     return (size_t)(v < 1 ? 1 : v > 64 ? 64 : v);
 }
 
@@ -237,7 +241,7 @@ int32_t p3gpu_coset_lde_batch(p3gpu_ctx *ctx, int field, const uint32_t *h_in, s
     P3_CHECK(h_in && h_out, P3GPU_EINVAL, "null argument");
     P3_CHECK(added_bits <= 8, P3GPU_EINVAL, "added_bits %u too large", added_bits);
     const size_t nin = h * w * 4, nout = nin << added_bits, H = h << added_bits;
-    const std::vector<size_t> cb = column_chunks(w, bitrev_rows && h >= 4096 ? host_chunk_count(nin) : 1);
+    const std::vector<size_t> cb = column_chunks(w, bitrev_rows && h >= 4096 ? host_chunk_count(nin, 1) : 1);
     if (cb.size() == 2) {                                   // one chunk: strictly serial H2D -> LDE -> D2H on the context's stream
         void *in = nullptr, *out = nullptr;
         P3_TRY(ctx_pool(ctx, 0, nin, &in));
@@ -461,6 +465,76 @@ int32_t p3gpu_open_reduce_dev(p3gpu_ctx *ctx, int field, uint32_t *d_ro, const u
     return open_reduce(ctx, field, d_ro, d_r, d_inv_denoms, h, coeff, yred);
 }
 
+// ---- Poseidon2 AIR: trace generation + quotient --------------------------------
+int32_t p3gpu_p2air_set_constants(p3gpu_ctx *ctx, int field, const uint32_t *beginning_full, const uint32_t *partial, int rounds_p,
+                                  const uint32_t *ending_full) {
+    P3_ENTER(ctx);
+    P3_CHECK(beginning_full && partial && ending_full, P3GPU_EINVAL, "null argument");
+    return air_set_constants(ctx, field, beginning_full, partial, rounds_p, ending_full);
+}
+size_t p3gpu_p2air_columns(int rounds_p) { return 144 + (size_t)rounds_p; }
+int32_t p3gpu_p2air_generate_trace_dev(p3gpu_ctx *ctx, int field, const uint32_t *d_inputs, size_t n_perms, uint32_t *d_trace) {
+    P3_ENTER(ctx);
+    P3_CHECK(d_inputs && d_trace, P3GPU_EINVAL, "null argument");
+    return air_generate_trace(ctx, field, d_inputs, n_perms, d_trace);
+}
+int32_t p3gpu_p2air_quotient_dev(p3gpu_ctx *ctx, int field, int vector_len, const uint32_t *d_lde, unsigned log_lde_height, unsigned log_trace_height,
+                                 const uint32_t alpha[4], uint32_t *d_quotient) {
+    P3_ENTER(ctx);
+    P3_CHECK(d_lde && alpha && d_quotient, P3GPU_EINVAL, "null argument");
+    return air_quotient(ctx, field, vector_len, d_lde, log_lde_height, log_trace_height, alpha, d_quotient);
+}
+
+// ---- transcript + query phase (prove driver) ---------------------------------------------------------
+int32_t p3gpu_challenger_new(p3gpu_ctx *ctx, int field, int width, int rate, p3gpu_challenger **out) {
+    P3_ENTER(ctx);
+    P3_CHECK(out, P3GPU_EINVAL, "null argument");
+    return challenger_new(ctx, field, width, rate, out);
+}
+void p3gpu_challenger_free(p3gpu_ctx *ctx, p3gpu_challenger *ch) {
+    if (!ctx) return;
+    std::lock_guard<std::recursive_mutex> lock(ctx->call_mu);
+    cudaSetDevice(ctx->device);
+    challenger_free(ctx, ch);
+}
+int32_t p3gpu_challenger_clone(p3gpu_ctx *ctx, const p3gpu_challenger *src, p3gpu_challenger **out) {
+    P3_ENTER(ctx);
+    P3_CHECK(src && out, P3GPU_EINVAL, "null argument");
+    return challenger_clone(ctx, src, out);
+}
+int32_t p3gpu_challenger_observe_dev(p3gpu_ctx *ctx, p3gpu_challenger *ch, const uint32_t *d_values, size_t n) {
+    P3_ENTER(ctx);
+    P3_CHECK(ch && (d_values || n == 0), P3GPU_EINVAL, "null argument");
+    return challenger_observe_dev(ctx, ch, d_values, n);
+}
+int32_t p3gpu_challenger_observe(p3gpu_ctx *ctx, p3gpu_challenger *ch, const uint32_t *h_values, size_t n) {
+    P3_ENTER(ctx);
+    P3_CHECK(ch && (h_values || n == 0), P3GPU_EINVAL, "null argument");
+    return challenger_observe_host(ctx, ch, h_values, n);
+}
+int32_t p3gpu_challenger_sample(p3gpu_ctx *ctx, p3gpu_challenger *ch, uint32_t *h_out, size_t n) {
+    P3_ENTER(ctx);
+    P3_CHECK(ch && h_out, P3GPU_EINVAL, "null argument");
+    return challenger_sample(ctx, ch, h_out, n);
+}
+int32_t p3gpu_challenger_grind(p3gpu_ctx *ctx, p3gpu_challenger *ch, unsigned bits, uint32_t *witness) {
+    P3_ENTER(ctx);
+    P3_CHECK(ch && witness, P3GPU_EINVAL, "null argument");
+    return challenger_grind(ctx, ch, bits, witness);
+}
+int32_t p3gpu_gather_rows_dev(p3gpu_ctx *ctx, const uint32_t *d_mat, size_t h, size_t w, const uint32_t *h_indices, size_t n, unsigned index_shift,
+                              uint32_t *d_out) {
+    P3_ENTER(ctx);
+    P3_CHECK(d_mat && h_indices && d_out, P3GPU_EINVAL, "null argument");
+    return query_gather_rows(ctx, d_mat, h, w, h_indices, n, index_shift, d_out);
+}
+int32_t p3gpu_merkle_paths_dev(p3gpu_ctx *ctx, const uint32_t *d_layers, const size_t *layer_lens, size_t n_layers, size_t path_len,
+                               const uint32_t *h_indices, size_t n, unsigned index_shift, uint32_t *d_out) {
+    P3_ENTER(ctx);
+    P3_CHECK(d_layers && layer_lens && h_indices && d_out, P3GPU_EINVAL, "null argument");
+    return query_merkle_paths(ctx, d_layers, layer_lens, n_layers, path_len, h_indices, n, index_shift, d_out);
+}
+
 // ---- multi-GPU: CUDA IPC plumbing + the row-sharded commit ---------------------------------------
 int32_t p3gpu_ipc_export(p3gpu_ctx *ctx, void *dptr, uint8_t handle[64]) {
     P3_ENTER(ctx);
@@ -615,7 +689,7 @@ int32_t p3gpu_pcs_commit(p3gpu_ctx *ctx, int field, int hash, const uint32_t *h_
     P3_CHECK(field == BABY_BEAR || field == KOALA_BEAR, P3GPU_EUNSUPPORTED, "unknown field %d", field);
     const u32 shift = field == BABY_BEAR ? to_monty<BABY_BEAR>(Fp<BABY_BEAR>::GEN) : to_monty<KOALA_BEAR>(Fp<KOALA_BEAR>::GEN);
     const size_t nin = h * w * 4;
-    const std::vector<size_t> cb = column_chunks(w, h >= 4096 ? std::max<size_t>(host_chunk_count(nin), nin >> 29) : 1);   // <= 512 MB per chunk
+    const std::vector<size_t> cb = column_chunks(w, h >= 4096 ? std::max<size_t>(host_chunk_count(nin, 4), nin >> 29) : 1);   // <= 512 MB per chunk
     if (cb.size() == 2) {
         void *in = nullptr;
         P3_TRY(ctx_pool(ctx, 0, nin, &in));

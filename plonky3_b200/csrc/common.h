@@ -8,6 +8,7 @@
 #include <mutex>
 #include <string>
 #include <tuple>
+#include <type_traits>
 #include <vector>
 
 #include <cuda_runtime.h>
@@ -95,6 +96,8 @@ struct p3gpu_ctx {
     // Poseidon2 constants: [field][0: width 16, 1: width 24], host copy + device copy
     p3::Poseidon2Consts p2_host[2][2];
     p3::Poseidon2Consts *p2_dev = nullptr;  // 4 entries
+    alignas(8) unsigned char air_consts[1024];   // Poseidon2 AIR round constants (air.cu: AirConsts)
+    int air_set = 0;
 };
 
 namespace p3 {
@@ -132,6 +135,23 @@ int32_t ntt_coset_lde_sharded(p3gpu_ctx *ctx, int field, const u32 *d_in, size_t
                               unsigned world, u32 *const *rank_out, size_t w_total, size_t col_off);
 int32_t peer_barrier(p3gpu_ctx *ctx, unsigned world, unsigned rank, void *const *ctrl, u32 epoch, double timeout_s);
 int32_t peer_allgather(p3gpu_ctx *ctx, unsigned world, unsigned rank, void *const *tables, const u32 *d_src, size_t words);
+
+// air.cu: Poseidon2 AIR trace generation / quotient
+int32_t air_set_constants(p3gpu_ctx *ctx, int field, const u32 *beg, const u32 *part, int rounds_p, const u32 *end);
+int32_t air_generate_trace(p3gpu_ctx *ctx, int field, const u32 *d_inputs, size_t n_perms, u32 *d_trace);
+int32_t air_quotient(p3gpu_ctx *ctx, int field, int vec_len, const u32 *d_lde, unsigned log_h, unsigned log_n, const u32 *alpha, u32 *d_q);
+
+// challenger.cu / query.cu: transcript + query-phase gathers of the prove driver
+int32_t challenger_new(p3gpu_ctx *ctx, int field, int width, int rate, p3gpu_challenger **out);
+void challenger_free(p3gpu_ctx *ctx, p3gpu_challenger *ch);
+int32_t challenger_clone(p3gpu_ctx *ctx, const p3gpu_challenger *src, p3gpu_challenger **out);
+int32_t challenger_observe_dev(p3gpu_ctx *ctx, p3gpu_challenger *ch, const u32 *d_vals, size_t n);
+int32_t challenger_observe_host(p3gpu_ctx *ctx, p3gpu_challenger *ch, const u32 *h_vals, size_t n);
+int32_t challenger_sample(p3gpu_ctx *ctx, p3gpu_challenger *ch, u32 *h_out, size_t n);
+int32_t challenger_grind(p3gpu_ctx *ctx, p3gpu_challenger *ch, unsigned bits, u32 *witness_monty);
+int32_t query_gather_rows(p3gpu_ctx *ctx, const u32 *d_mat, size_t h, size_t w, const u32 *h_idx, size_t n, unsigned shift, u32 *d_out);
+int32_t query_merkle_paths(p3gpu_ctx *ctx, const u32 *d_layers, const size_t *layer_lens, size_t n_layers, size_t path_len, const u32 *h_idx,
+                           size_t n, unsigned shift, u32 *d_out);
 
 static inline unsigned log2_floor(size_t x) { unsigned l = 0; while ((x >> l) > 1) l++; return l; }
 static inline bool is_pow2(size_t x) { return x && !(x & (x - 1)); }

@@ -261,6 +261,32 @@ class Gpu:
         return lde, layers
 
 
+    # ------------------------------------------------------------------ Poseidon2 AIR
+    def p2air_set_constants(self, field, beginning_full, partial, ending_full):
+        a = np.ascontiguousarray(beginning_full, dtype=np.uint32).ravel()
+        b = np.ascontiguousarray(partial, dtype=np.uint32).ravel()
+        c = np.ascontiguousarray(ending_full, dtype=np.uint32).ravel()
+        assert a.size == 64 and c.size == 64
+        check(self.L.p3gpu_p2air_set_constants(self.h, field, a.ctypes.data, b.ctypes.data, b.size, c.ctypes.data))
+        self._air_cols = int(self.L.p3gpu_p2air_columns(b.size))
+
+    def p2air_generate_trace(self, field, inputs_dev, vector_len=8):
+        """(n_perms, 16) CUDA tensor -> vectorised trace (n_perms / vector_len, vector_len * columns)."""
+        x = self._dev(inputs_dev); self._use_torch_stream()
+        n = int(x.shape[0])
+        out = self._empty((n // vector_len, vector_len * self._air_cols))
+        check(self.L.p3gpu_p2air_generate_trace_dev(self.h, field, x.data_ptr(), n, out.data_ptr()))
+        return out
+
+    def p2air_quotient(self, field, lde_dev, log_trace_height, alpha, vector_len=8):
+        """quotient values (H, 4) in natural order over GENERATOR * K, |K| = H = LDE height."""
+        m = self._dev(lde_dev); self._use_torch_stream()
+        H = int(m.shape[0]); log_h = H.bit_length() - 1
+        assert int(m.shape[1]) == vector_len * self._air_cols
+        q = self._empty((H, 4))
+        check(self.L.p3gpu_p2air_quotient_dev(self.h, field, vector_len, m.data_ptr(), log_h, log_trace_height, self._ef(alpha).ctypes.data, q.data_ptr()))
+        return q
+
     def pcs_commit_host(self, field, hash_kind, evals_host, log_blowup, cap_height):
         """p3gpu_pcs_commit: TwoAdicFriPcs::commit with the trace in HOST memory (numpy uint32 array or pinned CPU int32 tensor);
         the LDE and the digest layers stay on the device, only the cap returns.  Returns (cap (n, 8) array, lde, layers)."""

@@ -108,3 +108,47 @@ class MerkleTreeMmcs:
             proof.append(_host(prover_data.digest_layers[layer_idx][(idx ^ 1):(idx ^ 1) + 1])[0])
             idx >>= 1
         return openings, proof
+
+    # commit/src/mmcs.rs:173 / merkle-tree/src/mmcs/mod.rs:276-428 (without the path pruning, which is a host-side re-encoding)
+    def open_multi_batch(self, indices, prover_data: MerkleTree):
+        """open_batch for many indices at once.  Returns (openings: per matrix an (n, width) uint32 array, paths: (n, path_len, 8)
+        uint32 array of sibling digests, bottom-up).  Device-resident prover data is gathered by two small kernels
+        (csrc/query.cu) and copied back once per matrix."""
+        import ctypes as C
+        idx = np.ascontiguousarray(indices, dtype=np.uint32)
+        n = int(idx.size)
+        max_height = self.get_max_height(prover_data)
+        if n and int(idx.max()) >= max_height:
+            raise IndexError(f"index {int(idx.max())} out of bounds for height {max_height}")
+        log_max = _log2_ceil(max_height)
+        gpu = self.gpu
+        openings = []
+        for m in prover_data.leaves:
+            shift = log_max - _log2_ceil(int(m.shape[0]))
+            if _is_torch(m) and m.is_cuda:
+                gpu._use_torch_stream()
+                out = gpu._empty((n, int(m.shape[1])))
+                _lib.check(gpu.L.p3gpu_gather_rows_dev(gpu.h, m.data_ptr(), int(m.shape[0]), int(m.shape[1]), idx.ctypes.data, n, shift, out.data_ptr()))
+                openings.append(_host(out))
+            else:
+                openings.append(np.array(_host(m)[idx >> shift], dtype=np.uint32))
+        nl = prover_data.num_layers()
+        eff = min(self.cap_height, max(nl - 1, 0))
+        path_len = nl - 1 - eff
+        layers = prover_data.digest_layers
+        if path_len == 0 or n == 0:
+            return openings, np.zeros((n, path_len, 8), dtype=np.uint32)
+        if _is_torch(layers[0]) and layers[0].is_cuda:
+            lens = (C.c_size_t * nl)(*[int(l.shape[0]) for l in layers])
+            base, off = layers[0].data_ptr(), 0
+            for l in layers:                                             # all layers of a commit are slices of one device buffer
+                assert l.data_ptr() == base + off * 32, "digest layers are not contiguous"
+                off += int(l.shape[0])
+            gpu._use_torch_stream()
+            out = gpu._empty((n, path_len, 8))
+            _lib.check(gpu.L.p3gpu_merkle_paths_dev(gpu.h, base, lens, nl, path_len, idx.ctypes.data, n, 0, out.data_ptr()))
+            return openings, _host(out)
+        paths = np.zeros((n, path_len, 8), dtype=np.uint32)
+        for l in range(path_len):
+            paths[:, l] = _host(layers[l])[(idx >> l) ^ 1]
+        return openings, paths

@@ -1,0 +1,119 @@
+"""uni-stark `prove` of the vectorised Poseidon2 AIR on the GPU (plonky3_b200.uni_stark, BASELINE config 5 at small sizes) against the
+CPU replay built from the oracle (tests/p2_prove_replay.py): every transcript-visible value — trace cap, quotient cap, opened
+values, FRI round caps, final polynomial, proof-of-work witness (smallest), query indices, every opened row and authentication
+path — bit for bit, with the example binary's constants (SmallRng seed 1: AIR round constants, Perm16, Perm24, in that order,
+examples/examples/prove_prime_field_31.rs:115,150,190-191) and its FRI parameters (new_benchmark_high_arity, cap_height 3)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import p3_oracle as O
+import p2_prove_replay as R
+
+from plonky3_b200 import _lib
+from plonky3_b200.dft import Radix2DitParallel
+from plonky3_b200.field import KoalaBear
+from plonky3_b200.fri import FriParameters, TwoAdicFriPcs
+from plonky3_b200.gpu import default_gpu
+from plonky3_b200.merkle_tree import MerkleTreeMmcs
+from plonky3_b200.poseidon2 import Poseidon2
+from plonky3_b200.uni_stark import RoundConstants, StarkConfig, VectorizedPoseidon2Air, prove
+
+pytestmark = pytest.mark.gpu
+f = KoalaBear
+
+
+def _gpu_perm(pm):
+    w = pm.width
+    return Poseidon2.new(f, w, np.array(pm.rc_init)[: 4 * w].reshape(4, w), np.array(pm.rc_term)[: 4 * w].reshape(4, w),
+                         np.array(pm.rc_int)[: pm.rounds_p], monty=True)
+
+
+@pytest.fixture(scope="module")
+def setup():
+    assert torch.cuda.is_available() and _lib.LIB_PATH.exists()
+    gpu = default_gpu(0)
+    rng = O.SmallRng(1)
+    oair = O.air_from_rng(f.id, rng)
+    o16 = O.perm_from_rng(f.id, 16, rng); o24 = O.perm_from_rng(f.id, 24, rng)
+    p16, p24 = _gpu_perm(o16), _gpu_perm(o24)
+    return gpu, oair, o16, o24, p16, p24
+
+
+def _config(gpu, p16, p24, num_queries, pow_bits):
+    mmcs = MerkleTreeMmcs.poseidon2(p16, p24, cap_height=3, gpu=gpu)                       # get_poseidon2_mmcs(perm16, perm24, 3)
+    fri = FriParameters(1, 0, 3, num_queries, 0, pow_bits, mmcs)                           # new_benchmark_high_arity
+    pcs = TwoAdicFriPcs(Radix2DitParallel(f, gpu), mmcs, fri)
+    return StarkConfig(pcs, p24, 16)
+
+
+@pytest.mark.parametrize("log_n,num_queries,pow_bits", [(4, 7, 5), (6, 100, 16), (9, 100, 8)])
+def test_prove_matches_cpu_replay(setup, log_n, num_queries, pow_bits):
+    gpu, oair, o16, o24, p16, p24 = setup
+    inputs = O.SmallRng(1).field(f.id, (8 << log_n) * 16).reshape(-1, 16)                  # generate_random_trace_rows' inputs
+    exp = R.prove(oair, o16, o24, inputs, num_queries=num_queries, query_pow_bits=pow_bits)
+    assert R.verify_constraints_at_zeta(oair, exp)
+    config = _config(gpu, p16, p24, num_queries, pow_bits)
+    air = VectorizedPoseidon2Air(f, RoundConstants(np.array(oair.beg).reshape(4, 16), np.array(oair.part)[: oair.rounds_p], np.array(oair.end).reshape(4, 16)), gpu)
+    trace = air.generate_trace_rows(torch.from_numpy(inputs.view(np.int32)).cuda())
+    proof = prove(config, air, trace)
+    assert proof.degree_bits == log_n
+    assert np.array_equal(proof.trace_commit, exp["trace_cap"])
+    assert np.array_equal(proof.quotient_commit, exp["quotient_cap"])
+    assert np.array_equal(proof.trace_local, exp["trace_local"])
+    for a, b in zip(proof.quotient_chunks, exp["quotient_chunks"]):
+        assert np.array_equal(a, b)
+    assert len(proof.commit_phase_commits) == len(exp["commit_phase_commits"])
+    for a, b in zip(proof.commit_phase_commits, exp["commit_phase_commits"]):
+        assert np.array_equal(a, b)
+    assert np.array_equal(proof.final_poly, exp["final_poly"])
+    assert proof.query_pow_witness == exp["query_pow_witness"]
+    assert proof.query_indices == exp["indices"]
+    for (rows, paths), (erows, epaths) in zip(proof.input_openings, exp["input_openings"]):
+        assert len(rows) == len(erows)
+        for a, b in zip(rows, erows):
+            assert np.array_equal(a, b)
+        assert np.array_equal(paths, epaths)
+    for (la, sib, paths), (ela, esib, epaths) in zip(proof.commit_phase_openings, exp["commit_phase_openings"]):
+        assert la == ela and np.array_equal(sib, esib) and np.array_equal(paths, epaths)
+    # the GPU proof satisfies the verifier's identity as well (same check on the GPU's own opened values)
+    mine = dict(exp, trace_local=proof.trace_local, quotient_chunks=proof.quotient_chunks)
+    assert R.verify_constraints_at_zeta(oair, mine)
+
+
+def test_challenger_matches_oracle(setup):
+    """DuplexChallenger on the device vs the oracle restatement: observe / sample interleavings, clone, grind."""
+    from plonky3_b200.challenger import DuplexChallenger
+    gpu, _, _, o24, _, p24 = setup
+    ch = DuplexChallenger(f, p24, 16, gpu)
+    oc = R.OracleChallenger(o24)
+    vals = O.random_matrix(f.id, 1, 200, seed=13)[0]
+    k = 0
+    for n_obs, n_smp in [(1, 1), (15, 2), (16, 0), (17, 5), (0, 20), (40, 3), (3, 0), (0, 1)]:
+        ch.observe_slice(vals[k:k + n_obs]); oc.observe_slice(vals[k:k + n_obs]); k += n_obs
+        got = ch.sample_many(n_smp) if n_smp else np.zeros(0, dtype=np.uint32)
+        assert list(got) == [oc.sample() for _ in range(n_smp)]
+    dv = torch.from_numpy(vals[100:150].view(np.int32)).cuda()
+    ch.observe_slice(dv); oc.observe_slice(vals[100:150])                              # device-resident observe
+    c2, o2 = ch.clone(), oc.clone()
+    for bits in (1, 7, 12):
+        assert ch.grind(bits) == oc.grind(bits)
+    assert ch.sample_bits(20) == oc.sample_bits(20)
+    assert c2.sample_bits(9) == o2.sample_bits(9)                                      # the clone kept the pre-grind state
+
+
+def test_open_multi_batch_matches_open_batch(setup):
+    gpu, _, _, _, p16, p24 = setup
+    mmcs = MerkleTreeMmcs.poseidon2(p16, p24, cap_height=2, gpu=gpu)
+    a = O.random_matrix(f.id, 256, 11, seed=1); b = O.random_matrix(f.id, 64, 5, seed=2)
+    dev = lambda m: torch.from_numpy(m.view(np.int32)).cuda()
+    _, tree = mmcs.commit([dev(a), dev(b)])
+    idx = [0, 1, 77, 255, 128, 77]
+    rows, paths = mmcs.open_multi_batch(idx, tree)
+    for q, i in enumerate(idx):
+        op, proof = mmcs.open_batch(i, tree)
+        assert np.array_equal(rows[0][q], op[0]) and np.array_equal(rows[1][q], op[1])
+        assert np.array_equal(paths[q], np.array(proof))
+    _, htree = mmcs.commit([a, b])                                                      # host-resident prover data
+    hrows, hpaths = mmcs.open_multi_batch(idx, htree)
+    assert all(np.array_equal(x, y) for x, y in zip(rows, hrows)) and np.array_equal(paths, hpaths)

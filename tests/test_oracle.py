@@ -294,3 +294,45 @@ def test_fixture_replay_with_oracle():
     got = FR.replay(OracleBackend())
     for k, v in got.items():
         assert v == gold[k], k
+
+
+# ---------------------------------------------------------------- Poseidon2 AIR + prove replay
+def test_smallrng_c_matches_fixture_pinned_python():
+    """the C SmallRng + field sampler equals the Python one that reproduces the reference's proof fixture (fixture_replay.py)."""
+    import fixture_replay as FR
+    py = FR.SmallRng(1)
+    # FR samples BabyBear (P of the fixture); draw the same stream with the C sampler for BabyBear
+    exp = [py.field_monty() for _ in range(300)]
+    assert list(O.SmallRng(1).field(0, 300)) == exp
+
+
+def test_poseidon2_air_trace_and_quotient():
+    rng = O.SmallRng(1)
+    air = O.air_from_rng(1, rng)
+    assert O.p2air_cols(air) == 164 and O.p2air_constraints(air) == 148           # 8 x 164 = 1312 columns (SURVEY 8d)
+    inputs = O.SmallRng(1).field(1, 64 * 16).reshape(64, 16)
+    trace = O.p2air_generate(air, inputs)
+    assert trace.shape == (8, 1312) and O.p2air_check(air, trace) == 0
+    # the last 16 columns of a permutation are the Poseidon2 output when the AIR constants are used as permutation constants
+    pm = O.make_perm(1, 16, np.array(air.beg), np.array(air.end), np.array(air.part)[:20], monty=True)
+    for p in (0, 5, 63):
+        row = trace.reshape(64, 164)[p]
+        assert np.array_equal(O.poseidon2_permute(pm, inputs[p]), row[148:])
+    lde = O.coset_lde_batch(1, trace, 1, O.generator(1), True)
+    alpha = O.random_matrix(1, 1, 4, seed=3)[0]
+    q = O.p2air_quotient(air, lde, 3, alpha)
+    assert not O.coset_idft_batch(1, q, O.generator(1))[14:].any()                 # deg Q <= 2N - 2
+    bad = trace.copy(); bad[2, 17] ^= 1
+    assert O.p2air_check(air, bad) > 0
+
+
+def test_prove_replay_satisfies_the_verifier_identity():
+    import p2_prove_replay as R
+    rng = O.SmallRng(1)
+    air = O.air_from_rng(1, rng)
+    p16 = O.perm_from_rng(1, 16, rng); p24 = O.perm_from_rng(1, 24, rng)
+    inputs = O.SmallRng(1).field(1, (8 << 3) * 16).reshape(-1, 16)
+    pr = R.prove(air, p16, p24, inputs, num_queries=4, query_pow_bits=4)
+    assert pr["log_arities"] == [3] and R.verify_constraints_at_zeta(air, pr)
+    broken = dict(pr, alpha=pr["zeta"])
+    assert not R.verify_constraints_at_zeta(air, broken)
