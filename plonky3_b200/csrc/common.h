@@ -85,7 +85,11 @@ struct p3gpu_ctx {
     cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
     cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr}, ev_start = nullptr;
     void *chunk_in[2] = {nullptr, nullptr}; size_t chunk_in_bytes[2] = {0, 0};
-    void *chunk_out[2] = {nullptr, nullptr}; size_t chunk_out_bytes[2] = {0, 0};   // device copy of the per-height matrix table (> 8 matrices)
+    void *chunk_out[2] = {nullptr, nullptr}; size_t chunk_out_bytes[2] = {0, 0};
+    // staged multi-GPU exchange: staging buffers (one LDE'd column chunk each), exchange stream and events
+    cudaStream_t xchg_stream = nullptr;
+    cudaEvent_t ev_stage_full[2] = {nullptr, nullptr}, ev_stage_free[2] = {nullptr, nullptr};
+    void *stage_buf[2] = {nullptr, nullptr}; size_t stage_bytes[2] = {0, 0};   // device copy of the per-height matrix table (> 8 matrices)
     // FRI half-inverse-power tables (bit-reversed), one per field, grown on demand
     uint32_t *fold_table[2] = {nullptr, nullptr};
     size_t fold_table_len[2] = {0, 0};
@@ -133,6 +137,8 @@ int32_t open_reduce(p3gpu_ctx *ctx, int field, u32 *d_ro, const u32 *d_r, const 
 // ntt.cu / peer.cu: multi-GPU
 int32_t ntt_coset_lde_sharded(p3gpu_ctx *ctx, int field, const u32 *d_in, size_t h, size_t w_local, unsigned added_bits, u32 shift,
                               unsigned world, u32 *const *rank_out, size_t w_total, size_t col_off);
+int32_t peer_push_rows(p3gpu_ctx *ctx, cudaStream_t stream, unsigned world, u32 *const *rows, const u32 *d_src, size_t H, size_t wc, size_t w_total,
+                       size_t dst_col, unsigned log_rows);
 int32_t peer_barrier(p3gpu_ctx *ctx, unsigned world, unsigned rank, void *const *ctrl, u32 epoch, double timeout_s);
 int32_t peer_allgather(p3gpu_ctx *ctx, unsigned world, unsigned rank, void *const *tables, const u32 *d_src, size_t words);
 

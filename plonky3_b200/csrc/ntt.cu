@@ -29,6 +29,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <vector>
 
 #include <cuda.h>   // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint, no libcuda link)
 
@@ -1283,10 +1284,57 @@ int32_t ntt_coset_lde_sharded(p3gpu_ctx *ctx, int field, const u32 *d_in, size_t
     // a tile of the last pass (2^r consecutive rows, r <= 10) must not straddle two ranks
     P3_CHECK(sh.log_rows >= 10 && sh.log_rows <= 31, P3GPU_EUNSUPPORTED, "sharded LDE needs at least 1024 rows per rank (have 2^%u)", sh.log_rows);
     for (unsigned g = 0; g < world; g++) { P3_CHECK(rank_out[g] != nullptr, P3GPU_EINVAL, "null output block for rank %u", g); sh.out[g] = rank_out[g]; }
-    bool done = false;
-    if (field == BABY_BEAR) P3_TRY(lde_tiled_impl<BABY_BEAR>(ctx, d_in, h, w_local, added_bits, shift, nullptr, &done, &sh));
-    else P3_TRY(lde_tiled_impl<KOALA_BEAR>(ctx, d_in, h, w_local, added_bits, shift, nullptr, &done, &sh));
-    P3_CHECK(done, P3GPU_EUNSUPPORTED, "sharded LDE needs the pipelined tiled path: width %% 4 == 0, width >= 8, 16-byte aligned input, 2^12 <= height");
+    // Two ways to get the result into the row blocks (P3GPU_SHARD_MODE):
+    //   fused  : the last pass of the transform stores every tile straight into the owner's row block (32-byte segments over NVLink)
+    //   staged : (default) the transform runs column chunk by column chunk into a local staging buffer; as soon as a chunk is done a
+    //            push kernel on a second stream copies its row blocks to their owners with 16-byte-per-lane coalesced stores while the
+    //            next chunk is transformed.  Measured at N = 2 (profiles/r02*_bench_n2.json): the 32-byte peer stores of the fused
+    //            variant make its last pass NVLink-bound (180-400 GB/s per GPU); 128-byte lines reach the peer-copy rate.
+    const char *mode = getenv("P3GPU_SHARD_MODE");
+    if (mode && strcmp(mode, "fused") == 0) {
+        bool done = false;
+        if (field == BABY_BEAR) P3_TRY(lde_tiled_impl<BABY_BEAR>(ctx, d_in, h, w_local, added_bits, shift, nullptr, &done, &sh));
+        else P3_TRY(lde_tiled_impl<KOALA_BEAR>(ctx, d_in, h, w_local, added_bits, shift, nullptr, &done, &sh));
+        P3_CHECK(done, P3GPU_EUNSUPPORTED, "sharded LDE needs the pipelined tiled path: width %% 4 == 0, width >= 8, 16-byte aligned input, 2^12 <= height");
+        return P3GPU_OK;
+    }
+    P3_CHECK(w_local % 4 == 0 && w_total % 4 == 0 && col_off % 4 == 0, P3GPU_EUNSUPPORTED, "sharded LDE: column blocks must be multiples of 4 columns");
+    if (!ctx->xchg_stream) {
+        P3_CUDA(cudaStreamCreateWithFlags(&ctx->xchg_stream, cudaStreamNonBlocking));
+        for (int b = 0; b < 2; b++) {
+            P3_CUDA(cudaEventCreateWithFlags(&ctx->ev_stage_full[b], cudaEventDisableTiming));
+            P3_CUDA(cudaEventCreateWithFlags(&ctx->ev_stage_free[b], cudaEventDisableTiming));
+        }
+    }
+    size_t chunk = (size_t)std::max(8, env_int("P3GPU_SHARD_CHUNK", 48) & ~7);
+    const size_t n_chunks = std::max<size_t>(1, (w_local + chunk / 2) / chunk);
+    std::vector<size_t> cb{0};
+    for (size_t c = 1; c <= n_chunks; c++) cb.push_back(c == n_chunks ? w_local : (w_local * c / n_chunks) & ~(size_t)7);
+    size_t wmax = 0;
+    for (size_t c = 0; c + 1 < cb.size(); c++) wmax = std::max(wmax, cb[c + 1] - cb[c]);
+    for (int b = 0; b < 2; b++) {
+        if (ctx->stage_bytes[b] < H * wmax * 4) {
+            if (ctx->stage_buf[b]) { P3_CUDA(cudaDeviceSynchronize()); P3_CUDA(cudaFree(ctx->stage_buf[b])); ctx->stage_buf[b] = nullptr; ctx->stage_bytes[b] = 0; }
+            cudaError_t e = cudaMalloc(&ctx->stage_buf[b], H * wmax * 4);
+            if (e != cudaSuccess) { set_error("cudaMalloc(%zu) failed: %s", H * wmax * 4, cudaGetErrorString(e)); cudaGetLastError(); return P3GPU_ENOMEM; }
+            ctx->stage_bytes[b] = H * wmax * 4;
+        }
+    }
+    for (size_t c = 0; c + 1 < cb.size(); c++) {
+        const int b = (int)(c & 1);
+        const size_t c0 = cb[c], wc = cb[c + 1] - c0;
+        if (wc == 0) continue;
+        if (c >= 2) P3_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_stage_free[b], 0));      // the push of chunk c-2 has drained this buffer
+        u32 *S = (u32 *)ctx->stage_buf[b];
+        if (field == BABY_BEAR) P3_TRY(coset_lde_impl<BABY_BEAR>(ctx, d_in + c0, h, wc, added_bits, shift, S, 1, w_local, wc));
+        else P3_TRY(coset_lde_impl<KOALA_BEAR>(ctx, d_in + c0, h, wc, added_bits, shift, S, 1, w_local, wc));
+        P3_CUDA(cudaEventRecord(ctx->ev_stage_full[b], ctx->stream));
+        P3_CUDA(cudaStreamWaitEvent(ctx->xchg_stream, ctx->ev_stage_full[b], 0));
+        P3_TRY(peer_push_rows(ctx, ctx->xchg_stream, world, rank_out, S, H, wc, w_total, col_off + c0, sh.log_rows));
+        P3_CUDA(cudaEventRecord(ctx->ev_stage_free[b], ctx->xchg_stream));
+    }
+    // whatever follows on the context's stream (the barrier) comes after the last pushes
+    for (int b = 0; b < 2; b++) P3_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_stage_free[b], 0));
     return P3GPU_OK;
 }
 
