@@ -51,8 +51,26 @@ def ef_inv(field: Field, a):
 
 
 def ef_dot_powers(field: Field, alpha, ys):
-    """sum_i alpha^i * ys[i] (dot_product(alpha.powers(), openings), two_adic_pcs.rs:636-637)."""
-    acc, pw = np.zeros(4, dtype=np.uint32), ef_one(field)
-    for y in ys:
-        acc = ef_add(field, acc, ef_mul(field, pw, y)); pw = ef_mul(field, pw, alpha)
-    return acc
+    """sum_i alpha^i * ys[i] (dot_product(alpha.powers(), openings), two_adic_pcs.rs:636-637): Horner on canonical integers."""
+    p, w = field.P, field.EXT_W
+    a = _c(field, alpha)
+    acc = [0, 0, 0, 0]
+    for y in reversed([_c(field, v) for v in np.asarray(ys, dtype=np.uint32).reshape(-1, 4)]):
+        r = [0] * 7
+        for i in range(4):
+            for j in range(4):
+                r[i + j] += acc[i] * a[j]
+        acc = [(r[0] + w * r[4] + y[0]) % p, (r[1] + w * r[5] + y[1]) % p, (r[2] + w * r[6] + y[2]) % p, (r[3] + y[3]) % p]
+    return _m(field, acc)
+
+
+def ef_from_basis_rows(field: Field, rows):
+    """sum_k X^k * rows[k] for 4 EF4 values (from_ext_basis_coefficients): X * (a0, a1, a2, a3) = (W a3, a0, a1, a2)."""
+    p, w = field.P, field.EXT_W
+    acc = [0, 0, 0, 0]
+    for k, r in enumerate(np.asarray(rows, dtype=np.uint32).reshape(4, 4)):
+        v = _c(field, r)
+        for _ in range(k):
+            v = [w * v[3] % p, v[0], v[1], v[2]]
+        acc = [(x + y) % p for x, y in zip(acc, v)]
+    return _m(field, acc)

@@ -7,6 +7,17 @@ from dataclasses import dataclass
 import numpy as np
 
 
+_RINV = {}
+
+
+def _rinv(p: int) -> int:
+    """2^-32 mod p, cached (every Montgomery <-> canonical conversion of the host-side scalar code needs it)."""
+    r = _RINV.get(p)
+    if r is None:
+        r = _RINV[p] = pow(1 << 32, p - 2, p)
+    return r
+
+
 @dataclass(frozen=True)
 class Field:
     id: int            # P3GPU_BABY_BEAR / P3GPU_KOALA_BEAR
@@ -20,7 +31,7 @@ class Field:
 
     # ---- canonical <-> Montgomery
     def to_monty(self, x: int) -> int: return (x % self.P) * (1 << 32) % self.P
-    def from_monty(self, m: int) -> int: return m * pow(1 << 32, self.P - 2, self.P) % self.P
+    def from_monty(self, m: int) -> int: return m * _rinv(self.P) % self.P
     @property
     def ONE(self) -> int: return self.to_monty(1)
 
@@ -29,7 +40,7 @@ class Field:
         return ((a << np.uint64(32)) % np.uint64(self.P)).astype(np.uint32)
 
     def from_monty_array(self, a) -> np.ndarray:
-        rinv = pow(1 << 32, self.P - 2, self.P)
+        rinv = _rinv(self.P)
         a = np.asarray(a, dtype=np.uint64)
         return (a * np.uint64(rinv) % np.uint64(self.P)).astype(np.uint32)
 

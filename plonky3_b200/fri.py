@@ -212,39 +212,44 @@ class TwoAdicFriPcs:
         for k, lh in max_lh.items():
             z = np.array(k, dtype=np.uint32)
             inv_denoms[k], adjusted[k] = gpu.open_inv_denoms(f.id, lh, z, X.ef_inv(f, z))
-        # opened values by barycentric interpolation of the low coset (:496-563; interpolation.rs:161-193)
-        all_opened = []
+        # opened values by barycentric interpolation of the low coset (:496-563; interpolation.rs:161-193).  The values stay on the
+        # device for the transcript (observed there) and for Mred(z); one small copy brings them back for the proof.
+        all_opened, opened_dev = [], []
         for mats, points in rounds:
-            per_mat = []
+            per_mat, per_mat_dev = [], []
             for m, pts in zip(mats, points):
                 h = int(m.shape[0]) >> self.fri.log_blowup
                 log_h = _log2_strict(h)
-                per_pt = []
+                per_pt, per_pt_dev = [], []
                 for z in pts:
                     k = tuple(int(v) for v in z)
                     z = np.array(k, dtype=np.uint32)
                     g_pow_n = f.pow(f.generator, h)
                     denom_inv = f.inv(f.mul(g_pow_n, f.to_monty(h)))
                     scal = X.ef_scale(f, X.ef_mul(f, z, X.ef_sub(f, X.ef_pow(f, z, 1 << log_h), X.ef_from_base(f, g_pow_n))), denom_inv)
-                    ys = gpu.columnwise_dot(f.id, m[:h], adjusted[k], scal).cpu().numpy().view(np.uint32)
-                    challenger.observe_algebra_slice(ys)
-                    per_pt.append(ys)
-                per_mat.append(per_pt)
-            all_opened.append(per_mat)
+                    ys_dev = gpu.columnwise_dot(f.id, m[:h], adjusted[k], scal)
+                    challenger.observe_algebra_slice(ys_dev)
+                    per_pt_dev.append(ys_dev)
+                    per_pt.append(ys_dev.cpu().numpy().view(np.uint32))
+                per_mat.append(per_pt); per_mat_dev.append(per_pt_dev)
+            all_opened.append(per_mat); opened_dev.append(per_mat_dev)
         alpha = np.asarray(challenger.sample_algebra_element(), dtype=np.uint32)
         # reduced openings per height (:598-660)
         num_reduced, reduced = {}, {}
-        for (mats, points), opened_round in zip(rounds, all_opened):
+        for (mats, points), opened_round in zip(rounds, opened_dev):
             for m, pts, opened_mat in zip(mats, points, opened_round):
                 H = int(m.shape[0]); lh = _log2_strict(H)
                 if lh not in reduced:
                     reduced[lh] = torch.zeros((H, 4), dtype=torch.int32, device=m.device)
                     num_reduced[lh] = 0
                 r = gpu.rowwise_dot(f.id, m, alpha)                              # Mred(x) for every row
-                for z, ys in zip(pts, opened_mat):
+                for z, ys_dev in zip(pts, opened_mat):
                     k = tuple(int(v) for v in z)
                     coeff = X.ef_pow(f, alpha, num_reduced[lh])                  # alpha_pow_offset
-                    yred = X.ef_dot_powers(f, alpha, ys)                         # Mred(z)
+                    # Mred(z) = sum_i alpha^i y_i: the same row-wise dot kernel on the 4 coefficient rows of the opened values,
+                    # recombined with the basis (1, X, X^2, X^3) on the host
+                    yt = ys_dev.t().contiguous()                                 # (4, width)
+                    yred = X.ef_from_basis_rows(f, gpu.rowwise_dot(f.id, yt, alpha).cpu().numpy().view(np.uint32))
                     gpu.open_reduce(f.id, reduced[lh], r, inv_denoms[k], coeff, yred)
                     num_reduced[lh] += int(m.shape[1])
         fri_inputs = [reduced[lh] for lh in sorted(reduced, reverse=True)]

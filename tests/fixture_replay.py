@@ -215,6 +215,8 @@ def replay(backend):
     if hasattr(backend, "open"):
         class _Adapter:                                                # challenger protocol of plonky3_b200.fri
             def observe_algebra_slice(self, ys):
+                if hasattr(ys, "cpu"):                                 # device-resident opened values
+                    ys = ys.cpu().numpy().view(np.uint32)
                 for y in np.asarray(ys).reshape(-1, 4):
                     for v in y: ch.observe(from_m(int(v)))
             def sample_algebra_element(self): return [to_m(v) for v in ch.sample_ef()]

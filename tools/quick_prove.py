@@ -1,0 +1,36 @@
+"""Times uni-stark prove of the config-5 statement (2^L rows x 1312 columns) on cuda:0 and prints the span breakdown.
+Usage: python tools/quick_prove.py [log_trace_length=20] [reps=3]"""
+import json
+import pathlib
+import sys
+import time
+
+import numpy as np
+import torch
+
+sys.path.insert(0, str(pathlib.Path(__file__).resolve().parent.parent))
+from plonky3_b200.dft import Radix2DitParallel
+from plonky3_b200.field import KoalaBear as KB
+from plonky3_b200.fri import FriParameters, TwoAdicFriPcs
+from plonky3_b200.gpu import default_gpu
+from plonky3_b200.merkle_tree import MerkleTreeMmcs
+from plonky3_b200.poseidon2 import default_poseidon2
+from plonky3_b200.uni_stark import RoundConstants, StarkConfig, VectorizedPoseidon2Air, prove
+
+L = int(sys.argv[1]) if len(sys.argv) > 1 else 20
+reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+gpu = default_gpu(0)
+mm = MerkleTreeMmcs.poseidon2(default_poseidon2(KB, 16), default_poseidon2(KB, 24), 3, gpu)
+cfg = StarkConfig(TwoAdicFriPcs(Radix2DitParallel(KB, gpu), mm, FriParameters.new_benchmark_high_arity(mm)), default_poseidon2(KB, 24), 16)
+rs = np.random.default_rng(7)
+air = VectorizedPoseidon2Air(KB, RoundConstants(rs.integers(0, KB.P, (4, 16), dtype=np.uint32), rs.integers(0, KB.P, 20, dtype=np.uint32),
+                                                rs.integers(0, KB.P, (4, 16), dtype=np.uint32)), gpu)
+inputs = torch.randint(0, KB.P, (8 << L, 16), device="cuda", dtype=torch.int32)
+trace = air.generate_trace_rows(inputs)
+del inputs
+prove(cfg, air, trace)
+torch.cuda.synchronize(); t0 = time.perf_counter()
+for _ in range(reps):
+    p = prove(cfg, air, trace)
+torch.cuda.synchronize()
+print(json.dumps({"log_trace_length": L, "prove_ms": (time.perf_counter() - t0) * 1e3 / reps, "spans_ms": p.timings_ms}))
