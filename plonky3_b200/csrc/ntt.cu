@@ -83,6 +83,7 @@ struct PassArgs {
     // column blocks into row blocks happens in the pass's own stores, tile by tile, over NVLink.
     u32 *shard_out[16];
     int shard_log_rows;   // 0 = off
+    u32 half_sector;      // ntt_pass_runs_kernel: the output pitch is 16 mod 32 bytes and the base is 32-byte aligned (zero-fill trick)
 };
 
 template <int LOG_CT> __device__ __forceinline__ u32 sidx(u32 row, u32 c) {
@@ -686,6 +687,180 @@ __global__ void __launch_bounds__(NGROUP * GTHREADS + 32, 1) ntt_pass_pipe_kerne
     }
 }
 
+// ---- last pass into a half-sector pitch: group-owned units + full-sector stores --------------------------------------------
+// The LDE's last pass writes the caller's dense layout.  With a row pitch of 16 mod 32 bytes (w = 100, 300: w % 8 == 4) every odd
+// row starts in the middle of a 32-byte sector, so each 32-byte tile segment of an odd row is two HALF sectors — partial-sector
+// writes that cost the L2 a read-modify-write and, when they miss, a DRAM fill (638 vs 457 us for the same work into an aligned
+// layout, profiles/README.md).  This variant of the pipelined kernel removes them:
+//   * each consumer group owns a whole (row tile, coset) unit and walks its column tiles in order (the CTA interleaves NGROUP units:
+//     tile sequence = (ct 0, unit 0..NGROUP-1), (ct 1, unit 0..NGROUP-1), ... so the stage ring is used exactly as before), with one
+//     twiddle buffer per group;
+//   * in an odd row, lanes c >= 4 of tile k hold the FIRST half of a sector whose second half belongs to lanes c < 4 of tile k + 1.
+//     The same thread processes both tiles in program order, so tile k writes that whole sector in ONE store instruction (real data
+//     in the first half, zeros in the second) and tile k + 1 later overwrites its half: a 16-byte write into a sector that is
+//     already complete in the L2.  Every sector is thus first touched by a full-sector write: no fills, no partial-write misses.
+// Non-permuted input (tiled layout), dense natural-order output only: exactly the last pass of lde_tiled_impl.
+template <int F, int R_LOG, int NSTAGE, int NGROUP, int GTHREADS>
+__global__ void __launch_bounds__(NGROUP * GTHREADS + 32, 1) ntt_pass_runs_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ PassArgs a) {
+    constexpr u32 CT = 8;
+    constexpr int Q2 = (R_LOG + 1) / 2, Q1 = R_LOG - Q2;
+    constexpr u32 E1 = 1u << Q1, E2 = 1u << Q2, R = 1u << R_LOG;
+    constexpr u32 GS = E2, NG = E1;
+    constexpr u32 gstride = (GS + 1) * CT;
+    constexpr u32 STAGE_WORDS = NG * gstride;
+    constexpr u32 BOX_BYTES = STAGE_WORDS * 4;
+    static_assert(BOX_BYTES % 128 == 0, "stage alignment");
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    u32 *stages = reinterpret_cast<u32 *>(smem_raw);
+    uint2 *tws0 = reinterpret_cast<uint2 *>(smem_raw + (size_t)NSTAGE * BOX_BYTES);
+    const u32 bar0 = (u32)__cvta_generic_to_shared(smem_raw + (size_t)NSTAGE * BOX_BYTES + (size_t)NGROUP * R * sizeof(uint2));
+    auto full_bar = [&](u32 s) { return bar0 + 8u * s; };
+    auto empty_bar = [&](u32 s) { return bar0 + 8u * (NSTAGE + s); };
+    auto twfull_bar = [&](u32 j) { return bar0 + 8u * (2 * NSTAGE + j); };
+    auto twempty_bar = [&](u32 j) { return bar0 + 8u * (2 * NSTAGE + NGROUP + j); };
+
+    if (threadIdx.x == 0) {
+        for (u32 s = 0; s < NSTAGE; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), NGROUP * GTHREADS); }
+        for (u32 j = 0; j < NGROUP; j++) { mbar_init(twfull_bar(j), 1); mbar_init(twempty_bar(j), GTHREADS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const int lowbits = a.log_n - a.l1;
+    auto decode = [&](u32 unit, u32 &coset, u32 &L, u32 &T) {
+        coset = unit % a.n_cosets;
+        const u32 tile = unit / a.n_cosets;
+        L = tile & ((1u << lowbits) - 1u);
+        T = tile >> lowbits;
+    };
+    const u32 n_super = (a.n_items + NGROUP - 1) / NGROUP;
+
+    if (threadIdx.x >= NGROUP * GTHREADS) {
+        // ---------------- producer ----------------
+        if ((threadIdx.x & 31u) != 0) return;
+        u32 q = 0, ui = 0;
+        for (u32 si = blockIdx.x; si < n_super; si += gridDim.x, ui++) {
+            const u32 nj = min((u32)NGROUP, a.n_items - si * NGROUP);
+            int c3[NGROUP], c4[NGROUP];
+            for (u32 j = 0; j < nj; j++) {
+                u32 coset, L, T;
+                decode(si * NGROUP + j, coset, L, T);
+                mbar_wait(twempty_bar(j), (ui & 1u) ^ 1u);      // group j is done with its previous unit's twiddles
+                const uint2 *tw = a.tw + (size_t)coset * a.tw_stride;
+                uint2 *tws = tws0 + j * R;
+                tws[1] = tw[((size_t)1 << a.l0) + T];
+                mbar_expect_tx(twfull_bar(j), 8u * (R - 2u));
+#pragma unroll 1
+                for (int lam = 1; lam < R_LOG; lam++) {
+                    const uint2 *src = tw + ((size_t)1 << (a.l0 + lam)) + ((size_t)T << lam);
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                 ::"r"((u32)__cvta_generic_to_shared(tws + (1u << lam))), "l"(src), "r"(8u << lam), "r"(twfull_bar(j)) : "memory");
+                }
+                const u32 in_block = a.in_blocks > 1 ? coset : 0u;
+                c3[j] = (int)L;
+                c4[j] = (int)T + (int)(in_block << a.l0);
+            }
+            for (u32 ct = 0; ct < a.n_ctiles; ct++)
+                for (u32 j = 0; j < nj; j++, q++) {
+                    const u32 s = q % NSTAGE, k = q / NSTAGE;
+                    mbar_wait(empty_bar(s), (k & 1u) ^ 1u);
+                    mbar_expect_tx(full_bar(s), BOX_BYTES);
+                    const int cc4 = c4[j] + (int)((ct * a.in_blocks) << a.l0);
+                    asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
+                                 ::"r"((u32)__cvta_generic_to_shared(stages + (size_t)s * STAGE_WORDS)), "l"(reinterpret_cast<unsigned long long>(&tmap)),
+                                   "r"(0), "r"(0), "r"(0), "r"(c3[j]), "r"(cc4), "r"(full_bar(s)) : "memory");
+                }
+        }
+        return;
+    }
+
+    // ---------------- consumers ----------------
+    const u32 gid = threadIdx.x / GTHREADS, tg = threadIdx.x - gid * GTHREADS;
+    const u32 ow = a.w;
+    const bool half_sector = a.half_sector != 0;
+    u32 q = 0, ui = 0;
+    for (u32 si = blockIdx.x; si < n_super; si += gridDim.x, ui++) {
+        const u32 nj = min((u32)NGROUP, a.n_items - si * NGROUP);
+        u32 coset = 0, L = 0, T = 0;
+        if (gid < nj) decode(si * NGROUP + gid, coset, L, T);
+        const uint2 *tws = tws0 + gid * R;
+        const u32 ibase = (a.l0 == 0 ? 0u : (T << (a.log_n - a.l0))) | L;
+        bool tw_ready = false;
+        for (u32 ct = 0; ct < a.n_ctiles; ct++)
+            for (u32 j = 0; j < nj; j++, q++) {
+                const u32 s = q % NSTAGE, k = q / NSTAGE;
+                mbar_wait(full_bar(s), k & 1u);                 // every group observes every stage phase (see ntt_pass_pipe_kernel)
+                if (j != gid) { mbar_arrive(empty_bar(s)); continue; }
+                if (!tw_ready) { mbar_wait(twfull_bar(gid), ui & 1u); tw_ready = true; }
+                const u32 col = ct * CT, cw = min(CT, a.wc - col);
+                u32 *data = stages + (size_t)s * STAGE_WORDS;
+                const u32 dg = GTHREADS / cw, dc = GTHREADS - dg * cw;
+                {   // ---- step 1 (in place): E1 values per item, Q1 layers
+                    u32 g = tg / cw, c = tg - g * cw;
+                    for (; g < E2; ) {
+                        u32 x[E1];
+                        u32 *sp = data + g * CT + c;
+#pragma unroll
+                        for (u32 m = 0; m < E1; m++) x[m] = sp[m * gstride];
+                        reg_network<F, Q1>(x, tws, 1u);
+#pragma unroll
+                        for (u32 m = 0; m < E1; m++) sp[m * gstride] = x[m];
+                        c += dc; g += dg;
+                        if (c >= cw) { c -= cw; g++; }
+                    }
+                }
+                asm volatile("bar.sync %0, %1;" ::"r"(gid + 1u), "r"((u32)GTHREADS) : "memory");
+                {   // ---- step 2: E2 values per item, Q2 layers, results straight to global memory (rows of a tile are contiguous)
+                    u32 *out = a.out + (size_t)coset * a.out_stride + col;
+                    // zero-filling the next tile's half sector is only sound when the SAME thread later writes the real data there:
+                    // this tile and the next are both full-width (identical thread -> (row, column) mapping)
+                    const bool fill_next = half_sector && cw == CT && (ct + 2) * CT <= a.wc;
+                    u32 g = tg / cw, c = tg - g * cw;
+                    bool released = false;
+                    for (; g < E1; ) {
+                        u32 x[E2];
+                        const u32 *sp = data + g * gstride + c;
+#pragma unroll
+                        for (u32 m = 0; m < E2; m++) x[m] = sp[m * CT];
+                        u32 gn = g + dg, cn = c + dc;
+                        if (cn >= cw) { cn -= cw; gn++; }
+                        if (gn >= E1) {
+                            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                            mbar_arrive(empty_bar(s));
+                            released = true;
+                        }
+                        reg_network<F, Q2>(x, tws, E1 + g);
+#pragma unroll
+                        for (u32 m = 0; m < E2; m++) x[m] = fp_reduce<F>(x[m]);
+                        const u32 row0 = ibase | (g << Q2);                       // lowbits == 0: the tile's rows are consecutive
+                        u32 *p = out + (size_t)row0 * ow + c;
+                        if (!half_sector || cw != CT) {
+#pragma unroll
+                            for (u32 m = 0; m < E2; m++) p[(size_t)m * ow] = x[m];
+                        } else {
+                            const bool lo = c < 4;                                  // even rows are sector aligned, odd rows start 16 bytes in
+                            u32 *pb = p + (lo ? 8 : 0);
+#pragma unroll
+                            for (u32 m = 0; m < E2; m++) {
+                                if ((m & 1u) == 0) { p[(size_t)m * ow] = x[m]; }
+                                else {
+                                    if (lo) p[(size_t)m * ow] = x[m];             // second half of a sector that is already complete
+                                    if (!lo || fill_next) pb[(size_t)m * ow] = lo ? 0u : x[m];   // one full-sector store: lanes 4-7 data, lanes 0-3 zeros
+                                }
+                            }
+                        }
+                        g = gn; c = cn;
+                    }
+                    if (!released) {
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        mbar_arrive(empty_bar(s));
+                    }
+                }
+            }
+        if (gid < nj) mbar_arrive(twempty_bar(gid));
+    }
+}
+
 // ---- twiddle heaps ---------------------------------------------------------------------------
 struct TwGenArgs {
     u32 sigma[32];  // sigma[l] = shift^(N/2^(l+1)), Montgomery
@@ -956,6 +1131,60 @@ static int32_t launch_pipe(p3gpu_ctx *ctx, const PassArgs &a) {
     }
 }
 
+// Last pass of the tiled LDE into the caller's dense layout with group-owned units (ntt_pass_runs_kernel).
+template <int F, int R_LOG>
+static int32_t launch_runs_r(p3gpu_ctx *ctx, PassArgs a) {
+    constexpr int NSTAGE = 5, NGROUP = 4, GTHREADS = 128;
+    constexpr int Q2 = (R_LOG + 1) / 2, Q1 = R_LOG - Q2;
+    constexpr size_t box_bytes = ((size_t)1 << Q1) * (((size_t)1 << Q2) + 1) * 8 * 4;
+    constexpr size_t smem = NSTAGE * box_bytes + NGROUP * ((size_t)1 << R_LOG) * sizeof(uint2) + (2 * NSTAGE + 2 * NGROUP) * 8;
+    static_assert(smem <= 227 * 1024, "runs NTT kernel: shared memory budget");
+    CUtensorMap tm;
+    if (a.wc == 0) a.wc = a.w;
+    if (a.in_blocks == 0) a.in_blocks = 1;
+    P3_TRY(make_pass_tensor_map(a, false, &tm));
+    a.n_ctiles = (a.wc + 7) / 8;
+    a.csplit = 1; a.tpi = a.n_ctiles;
+    const size_t units = ((size_t)1 << (a.log_n - R_LOG)) * a.n_cosets;
+    P3_CHECK(units < (1ull << 31), P3GPU_EINVAL, "ntt: too many tiles");
+    a.n_items = (u32)units;
+    auto kern = ntt_pass_runs_kernel<F, R_LOG, NSTAGE, NGROUP, GTHREADS>;
+    static bool attr_set[64] = {false};
+    if (!attr_set[ctx->device & 63]) {
+        P3_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set[ctx->device & 63] = true;
+    }
+    const size_t n_super = (units + NGROUP - 1) / NGROUP;
+    const size_t grid = std::min(n_super, (size_t)ctx->sm_count);
+    kern<<<(unsigned)grid, NGROUP * GTHREADS + 32, smem, ctx->stream>>>(tm, a);
+    ctx->launches++;
+    P3_CUDA(cudaGetLastError());
+    return P3GPU_OK;
+}
+// the kernel pays off when the pitch leaves odd rows half a sector off (w % 8 == 4) and there are enough units to give every
+// group of every SM its own; P3GPU_NTT_RUNS=0 switches it off, =2 forces it for aligned pitches too (tests)
+static bool runs_eligible(p3gpu_ctx *ctx, const PassArgs &a, size_t out_pitch) {
+    const int mode = env_int("P3GPU_NTT_RUNS", 1);
+    if (mode == 0 || a.in_tiled == 0 || a.out_tiled || a.out_bitrev || a.out_sh || a.out_add || a.shard_log_rows || a.has_scale) return false;
+    if (a.log_n != a.l1 || !a.final_reduce) return false;
+    const int r = a.l1 - a.l0;
+    if (r < 6 || r > 10) return false;
+    const size_t units = ((size_t)1 << (a.log_n - r)) * a.n_cosets;
+    if (mode == 2) return true;
+    if (units < 8 * (size_t)ctx->sm_count) return false;
+    return out_pitch % 8 == 4 && reinterpret_cast<uintptr_t>(a.out) % 32 == 0;
+}
+template <int F>
+static int32_t launch_runs(p3gpu_ctx *ctx, const PassArgs &a) {
+    switch (a.l1 - a.l0) {
+        case 6: return launch_runs_r<F, 6>(ctx, a);
+        case 7: return launch_runs_r<F, 7>(ctx, a);
+        case 8: return launch_runs_r<F, 8>(ctx, a);
+        case 9: return launch_runs_r<F, 9>(ctx, a);
+        default: return launch_runs_r<F, 10>(ctx, a);
+    }
+}
+
 // Column tile width of the fast kernel: all tiles of a launch share one width (a ragged last tile is allowed).
 // Prefer exact divisors that keep 16-byte alignment (16, 20, 24 columns = 64/80/96-byte row segments).
 static u32 choose_tile_width(u32 w) {
@@ -1186,6 +1415,11 @@ static int32_t lde_tiled_impl(p3gpu_ctx *ctx, const u32 *d_in, size_t h, size_t 
             }
             else if (k == plan.n_passes - 1) { a.out = d_out + col0; a.out_tiled = 0; a.out_stride = h * out_pitch; a.final_reduce = 1; }
             else { a.out = (u32 *)B; a.out_tiled = 1; }
+            if (k == plan.n_passes - 1 && !shard && runs_eligible(ctx, a, out_pitch)) {
+                a.half_sector = (out_pitch % 8 == 4 && reinterpret_cast<uintptr_t>(a.out) % 32 == 0 && (h * out_pitch) % 8 == 0) ? 1u : 0u;
+                P3_TRY(launch_runs<F>(ctx, a));
+                continue;
+            }
             P3_TRY(launch_pipe<F>(ctx, a));
         }
     }
@@ -1306,7 +1540,7 @@ int32_t ntt_coset_lde_sharded(p3gpu_ctx *ctx, int field, const u32 *d_in, size_t
             P3_CUDA(cudaEventCreateWithFlags(&ctx->ev_stage_free[b], cudaEventDisableTiming));
         }
     }
-    size_t chunk = (size_t)std::max(8, env_int("P3GPU_SHARD_CHUNK", 48) & ~7);
+    size_t chunk = (size_t)std::max(8, env_int("P3GPU_SHARD_CHUNK", 96) & ~7);
     const size_t n_chunks = std::max<size_t>(1, (w_local + chunk / 2) / chunk);
     std::vector<size_t> cb{0};
     for (size_t c = 1; c <= n_chunks; c++) cb.push_back(c == n_chunks ? w_local : (w_local * c / n_chunks) & ~(size_t)7);
@@ -1330,7 +1564,15 @@ int32_t ntt_coset_lde_sharded(p3gpu_ctx *ctx, int field, const u32 *d_in, size_t
         else P3_TRY(coset_lde_impl<KOALA_BEAR>(ctx, d_in + c0, h, wc, added_bits, shift, S, 1, w_local, wc));
         P3_CUDA(cudaEventRecord(ctx->ev_stage_full[b], ctx->stream));
         P3_CUDA(cudaStreamWaitEvent(ctx->xchg_stream, ctx->ev_stage_full[b], 0));
-        P3_TRY(peer_push_rows(ctx, ctx->xchg_stream, world, rank_out, S, H, wc, w_total, col_off + c0, sh.log_rows));
+        if (mode && strcmp(mode, "dma") == 0) {
+            // copy engines instead of the push kernel: one 2-D peer copy per destination rank (no SM resources, but narrow rows)
+            const size_t R = (size_t)1 << sh.log_rows;
+            for (unsigned q = 0; q < world; q++)
+                P3_CUDA(cudaMemcpy2DAsync(rank_out[q] + col_off + c0, w_total * 4, S + (size_t)q * R * wc, wc * 4, wc * 4, R, cudaMemcpyDeviceToDevice,
+                                          ctx->xchg_stream));
+        } else {
+            P3_TRY(peer_push_rows(ctx, ctx->xchg_stream, world, rank_out, S, H, wc, w_total, col_off + c0, sh.log_rows));
+        }
         P3_CUDA(cudaEventRecord(ctx->ev_stage_free[b], ctx->xchg_stream));
     }
     // whatever follows on the context's stream (the barrier) comes after the last pushes

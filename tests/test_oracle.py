@@ -336,3 +336,110 @@ def test_prove_replay_satisfies_the_verifier_identity():
     assert pr["log_arities"] == [3] and R.verify_constraints_at_zeta(air, pr)
     broken = dict(pr, alpha=pr["zeta"])
     assert not R.verify_constraints_at_zeta(air, broken)
+
+
+# ---------------------------------------------------------------- Keccak: second, independent formulation
+_K_RC = [1, 0x8082, 0x800000000000808a, 0x8000000080008000, 0x808b, 0x80000001, 0x8000000080008081, 0x8000000000008009, 0x8a, 0x88,
+         0x80008009, 0x8000000a, 0x8000808b, 0x800000000000008b, 0x8000000000008089, 0x8000000000008003, 0x8000000000008002,
+         0x8000000000000080, 0x800a, 0x800000008000000a, 0x8000000080008081, 0x8000000000008080, 0x80000001, 0x8000000080008008]
+_K_RHO = [[0, 1, 62, 28, 27], [36, 44, 6, 55, 20], [3, 10, 43, 25, 39], [41, 45, 15, 21, 8], [18, 2, 61, 56, 14]]     # avx512.rs:225-263, [y][x]
+_K_PI = [[(0, 0), (1, 1), (2, 2), (3, 3), (4, 4)], [(0, 3), (1, 4), (2, 0), (3, 1), (4, 2)], [(0, 1), (1, 2), (2, 3), (3, 4), (4, 0)],
+         [(0, 4), (1, 0), (2, 1), (3, 2), (4, 3)], [(0, 2), (1, 3), (2, 4), (3, 0), (4, 1)]]                            # avx512.rs:268-306
+_M64 = (1 << 64) - 1
+
+
+def _rol(x, r): return ((x << r) | (x >> (64 - r))) & _M64 if r else x
+
+
+def keccak_f_matrix_form(flat):
+    """Keccak-f[1600] as the reference's in-repo vector implementation states it (keccak/src/avx512.rs:40-365): the state as a
+    5x5 matrix state[y][x] = flat[5y + x], five SEPARATE steps per round (theta, rho, pi as an explicit index table, chi row by
+    row, iota) — structurally unlike the C oracle (flat lanes, fused rho-pi walk)."""
+    s = [[int(flat[5 * y + x]) for x in range(5)] for y in range(5)]
+    for rnd in range(24):
+        par = [s[0][x] ^ s[1][x] ^ s[2][x] ^ s[3][x] ^ s[4][x] for x in range(5)]                  # get_theta_parities
+        tp = [(par[(x + 4) % 5], _rol(par[(x + 1) % 5], 1)) for x in range(5)]
+        s = [[s[y][x] ^ tp[x][0] ^ tp[x][1] for x in range(5)] for y in range(5)]                   # theta
+        s = [[_rol(s[y][x], _K_RHO[y][x]) for x in range(5)] for y in range(5)]                     # rho
+        s = [[s[a][b] for (a, b) in row] for row in _K_PI]                                          # pi
+        s = [[row[x] ^ (~row[(x + 1) % 5] & _M64 & row[(x + 2) % 5]) for x in range(5)] for row in s]   # chi (ternary 0b11010010)
+        s[0][0] ^= _K_RC[rnd]                                                                       # iota
+    return [s[y][x] for y in range(5) for x in range(5)]
+
+
+def _keccak_leaf_second_formulation(row):
+    """SerializingHasher<PaddingFreeSponge<KeccakF,25,17,4>> (serializing_hasher.rs:48-59, integers.rs:494-509, sponge.rs:182-216)
+    restated on top of the matrix-form permutation."""
+    words = [int(row[i]) | (int(row[i + 1]) << 32 if i + 1 < len(row) else 0) for i in range(0, len(row), 2)]
+    st = [0] * 25
+    for c0 in range(0, len(words), 17):
+        blk = words[c0:c0 + 17]
+        st[:len(blk)] = blk                                 # overwrite; a partial last block leaves the remaining rate words as they are
+        st = keccak_f_matrix_form(st)
+    return st[:4]
+
+
+def _digest_words(d4):
+    return np.array([w for v in d4 for w in (v & 0xffffffff, v >> 32)], dtype=np.uint32)
+
+
+def test_keccak_f_second_formulation_agrees_with_oracle():
+    rs = np.random.default_rng(5)
+    for _ in range(6):
+        st = rs.integers(0, 1 << 63, 25, dtype=np.uint64) * np.uint64(2) + rs.integers(0, 2, 25, dtype=np.uint64)
+        assert [int(v) for v in O.keccak_f(st)] == keccak_f_matrix_form(st)
+    assert [int(v) for v in O.keccak_f(np.zeros(25, dtype=np.uint64))][:2] == [0xF1258F7940E1DDE7, 0x84D5CCF933C0478A]   # Keccak team KAT, zero state
+
+
+def test_keccak_mmcs_semantics_second_formulation():
+    """leaf hash (all block-boundary cases: odd widths, exactly 34 = one full rate, 35, 300 = config 4) and node compression of the
+    Keccak MMCS against the independent restatement."""
+    hs = O.keccak_hasher()
+    for w in (1, 2, 3, 33, 34, 35, 68, 69, 300):
+        row = O.random_matrix(0, 1, w, seed=w)[0]
+        assert np.array_equal(O.hash_row(hs, row), _digest_words(_keccak_leaf_second_formulation(row))), w
+    l, r = O.random_matrix(0, 1, 8, seed=1)[0], O.random_matrix(0, 1, 8, seed=2)[0]
+    # CompressionFunctionFromHasher<_, 2, 4>: sponge over the 8 u64 words left || right (compression.rs:60-70)
+    words = [int(l[i]) | int(l[i + 1]) << 32 for i in range(0, 8, 2)] + [int(r[i]) | int(r[i + 1]) << 32 for i in range(0, 8, 2)]
+    st = [0] * 25
+    st[:8] = words
+    assert np.array_equal(O.compress(hs, l, r), _digest_words(keccak_f_matrix_form(st)[:4]))
+
+
+# ---------------------------------------------------------------- second reference proof fixture: multi-matrix commitment
+def _batch_fixture_traces():
+    """mul_trace(32, 2) and fib_trace(0, 1, 32) of batch-stark/tests/simple.rs:118-134,317-341 (Montgomery words)."""
+    p = 0x78000001
+    rows, reps = 32, 2
+    w = reps * 3 + 1
+    mul = [[0] * w for _ in range(rows)]
+    for rep in range(reps):
+        a, b = 0, 1
+        for i in range(rows):
+            mul[i][rep * 3], mul[i][rep * 3 + 1], mul[i][rep * 3 + 2] = a, b, a * b % p
+            if i != rows - 1:
+                mul[i][w - 1] = b
+            a, b = b, (a + b) % p
+    fib = [[0, 1]]
+    for _ in range(rows - 1):
+        fib.append([fib[-1][1], (fib[-1][0] + fib[-1][1]) % p])
+    return O.to_monty_arr(0, np.array(mul, dtype=np.uint64)), O.to_monty_arr(0, np.array(fib, dtype=np.uint64))
+
+
+def batch_fixture_main_cap(lde, commit):
+    """main commitment of the batch proof: pcs.commit([(H, mul_trace), (H, fib_trace)]) (batch-stark/src/prover.rs:225-231)."""
+    mul, fib = _batch_fixture_traces()
+    g = O.generator(0)
+    return commit([lde(mul, 2, g), lde(fib, 2, g)])
+
+
+def test_batch_stark_fixture_main_commitment():
+    """The reference's committed batch proof pins the multi-matrix leaf rule (rows of all matrices of a height concatenated in input
+    order into one sponge, merkle_tree.rs:312-316) that the unlimited-matrix leaf kernel and the row-sharded commit rely on."""
+    gold = json.loads((GOLD / "batch_stark_two_adic_v1.json").read_text())
+    rng = O.SmallRng(777)
+    pm = O.perm_from_rng(0, 16, rng)                                   # make_two_adic_compat_config(777)
+    hs = O.poseidon2_hasher(pm, pm)
+    cap = batch_fixture_main_cap(lambda m, bits, s: O.coset_lde_batch(0, m, bits, s, bitrev_out=True),
+                                 lambda mats: O.merkle_cap(O.merkle_tree(hs, mats), 1))
+    assert cap.tolist() == gold["main_cap"]
