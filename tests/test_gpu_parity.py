@@ -645,14 +645,8 @@ def test_lde_last_pass_group_owned_units(gpu, f, log_h, w, added_bits, monkeypat
     assert torch.equal(got, ref)
     if log_h <= 14:
         assert np.array_equal(host(got), O.coset_lde_batch(f.id, host(x), added_bits, f.generator, bitrev_out=True))
-    # a column block of a wider buffer (pitch != width): the neighbouring columns must stay untouched
     if w % 8 == 4 and log_h <= 16:
         monkeypatch.setenv("P3GPU_NTT_RUNS", "2")
-        wide = torch.full(((1 << log_h) << added_bits, w + 24), -7, device="cuda", dtype=torch.int32)
-        _lib.check(gpu.L.p3gpu_ctx_set_stream(gpu.h, torch.cuda.current_stream().cuda_stream))
-        from plonky3_b200.gpu import Gpu  # noqa: F401
-        # (the pitch-aware entry is internal; exercised through p3gpu_pcs_commit's chunked path below)
-        m = host(x)
-        cap, lde, layers = gpu.pcs_commit_host(f.id, _lib.HASH_POSEIDON2_W16, m, added_bits, 0)
+        default_poseidon2(f, 16).upload(gpu)
+        cap, lde, layers = gpu.pcs_commit_host(f.id, _lib.HASH_POSEIDON2_W16, host(x), added_bits, 0)   # host-trace commit on the same kernel
         assert torch.equal(lde, ref)
-        del wide
