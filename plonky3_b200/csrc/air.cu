@@ -121,36 +121,53 @@ __global__ void __launch_bounds__(128) p2air_quotient_kernel(const QuotArgs a, c
         const u32 *c = a.lde + (m * lanes + v) * cols;
         // constraint j = v * nc + kk uses alpha^(n_all - 1 - j): walk the table downwards
         const uint4 *apv = ap + (n_all - 1 - v * nc);
+        // a permutation's 164 columns start 16-byte aligned (656 = 41 x 16 bytes): 16-byte loads throughout
+        const uint4 *c4 = reinterpret_cast<const uint4 *>(c);
         u32 s[AIR_W];
+        auto ld16 = [&](u32 (&dst)[AIR_W]) {
 #pragma unroll
-        for (int x = 0; x < AIR_W; x++) s[x] = __ldg(c + x);
-        c += 16;
+            for (int x = 0; x < 4; x++) { const uint4 v4 = __ldg(c4 + x); dst[4 * x] = v4.x; dst[4 * x + 1] = v4.y; dst[4 * x + 2] = v4.z; dst[4 * x + 3] = v4.w; }
+            c4 += 4;
+        };
+        ld16(s);
         mds_light<F, AIR_W>(s);
 #pragma unroll 1
         for (int r = 0; r < 4; r++) {
 #pragma unroll
             for (int x = 0; x < AIR_W; x++) s[x] = sbox<F>(fp_add<F>(s[x], k.beg[r * 16 + x]));
             mds_light<F, AIR_W>(s);
+            u32 post[AIR_W];
+            ld16(post);
 #pragma unroll
-            for (int x = 0; x < AIR_W; x++) { const u32 post = __ldg(c + x); qmac<F>(acc, fp_sub<F>(s[x], post), apv[-x]); s[x] = post; }
-            c += 16; apv -= 16;
+            for (int x = 0; x < AIR_W; x++) { qmac<F>(acc, fp_sub<F>(s[x], post[x]), apv[-x]); s[x] = post[x]; }
+            apv -= 16;
         }
+        {
+            const u32 *cp = reinterpret_cast<const u32 *>(c4);
 #pragma unroll 1
-        for (int r = 0; r < k.rounds_p; r++) {
-            const u32 x3 = sbox<F>(fp_add<F>(s[0], k.part[r]));
-            const u32 post = __ldg(c++);
-            qmac<F>(acc, fp_sub<F>(x3, post), *apv--);
-            s[0] = post;
-            air_internal_layer<F>(s);
+            for (int r = 0; r < k.rounds_p; r += 4) {           // rounds_p % 4 == 0 is checked by the host (20 for KoalaBear width 16)
+                const uint4 v4 = __ldg(reinterpret_cast<const uint4 *>(cp + r));
+                const u32 pv[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+                for (int t2 = 0; t2 < 4; t2++) {
+                    const u32 x3 = sbox<F>(fp_add<F>(s[0], k.part[r + t2]));
+                    qmac<F>(acc, fp_sub<F>(x3, pv[t2]), *apv--);
+                    s[0] = pv[t2];
+                    air_internal_layer<F>(s);
+                }
+            }
+            c4 = reinterpret_cast<const uint4 *>(cp + k.rounds_p);
         }
 #pragma unroll 1
         for (int r = 0; r < 4; r++) {
 #pragma unroll
             for (int x = 0; x < AIR_W; x++) s[x] = sbox<F>(fp_add<F>(s[x], k.end[r * 16 + x]));
             mds_light<F, AIR_W>(s);
+            u32 post[AIR_W];
+            ld16(post);
 #pragma unroll
-            for (int x = 0; x < AIR_W; x++) { const u32 post = __ldg(c + x); qmac<F>(acc, fp_sub<F>(s[x], post), apv[-x]); s[x] = post; }
-            c += 16; apv -= 16;
+            for (int x = 0; x < AIR_W; x++) { qmac<F>(acc, fp_sub<F>(s[x], post[x]), apv[-x]); s[x] = post[x]; }
+            apv -= 16;
         }
     }
     u32 r[4];
@@ -188,7 +205,7 @@ static int32_t air_consts(p3gpu_ctx *ctx, int field, const AirConsts **out) {
 
 int32_t air_set_constants(p3gpu_ctx *ctx, int field, const u32 *beg, const u32 *part, int rounds_p, const u32 *end) {
     P3_CHECK(field == KOALA_BEAR, P3GPU_EUNSUPPORTED, "Poseidon2 AIR: only the KoalaBear instance (degree-3 S-box, no S-box registers) is built");
-    P3_CHECK(rounds_p >= 1 && rounds_p <= 32, P3GPU_EINVAL, "rounds_p %d out of range", rounds_p);
+    P3_CHECK(rounds_p >= 4 && rounds_p <= 32 && rounds_p % 4 == 0, P3GPU_EINVAL, "rounds_p %d must be a multiple of 4 in 4..32", rounds_p);
     static_assert(sizeof(AirConsts) <= sizeof(ctx->air_consts), "context storage for the AIR constants");
     AirConsts k;
     memset(&k, 0, sizeof k);
@@ -219,6 +236,7 @@ int32_t air_quotient(p3gpu_ctx *ctx, int field, int vec_len, const u32 *d_lde, u
     P3_TRY(air_consts(ctx, field, &k));
     P3_CHECK(vec_len >= 1 && vec_len <= 32 && (vec_len & (vec_len - 1)) == 0, P3GPU_EINVAL, "vector length %d must be a power of two <= 32", vec_len);
     P3_CHECK(log_h >= log_n && log_h <= Fp<F>::TWO_ADICITY && log_h - log_n <= 8, P3GPU_EINVAL, "bad domain sizes 2^%u / 2^%u", log_h, log_n);
+    P3_CHECK(reinterpret_cast<uintptr_t>(d_lde) % 16 == 0 && reinterpret_cast<uintptr_t>(d_q) % 16 == 0, P3GPU_EINVAL, "quotient: buffers must be 16-byte aligned");
     const int nc = 128 + k->rounds_p, n_all = nc * vec_len;
     const unsigned rate_bits = log_h - log_n;
     const size_t nz = (size_t)1 << rate_bits;
