@@ -83,7 +83,7 @@ struct PassArgs {
     // column blocks into row blocks happens in the pass's own stores, tile by tile, over NVLink.
     u32 *shard_out[16];
     int shard_log_rows;   // 0 = off
-    u32 half_sector;      // ntt_pass_runs_kernel: the output pitch is 16 mod 32 bytes and the base is 32-byte aligned (zero-fill trick)
+    u32 half_sector;      // last pass, dense output pitch = 16 mod 32 bytes, 32-byte aligned base: column-tile runs + full-sector stores
 };
 
 template <int LOG_CT> __device__ __forceinline__ u32 sidx(u32 row, u32 c) {
@@ -471,8 +471,19 @@ __device__ __forceinline__ void mbar_arrive(u32 bar) { asm volatile("mbarrier.ar
 __device__ __forceinline__ void mbar_arrive_n(u32 bar, u32 n) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(n) : "memory"); }
 __device__ __forceinline__ void mbar_expect_tx(u32 bar, u32 bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory"); }
 
-template <int F, int R_LOG, bool PERM, int NSTAGE, int NGROUP, int GTHREADS>
+// HS (half-sector variant, last LDE pass only: dense natural-order output whose row pitch is 16 mod 32 bytes, e.g. w = 100, 300):
+// every odd row starts in the middle of a 32-byte sector, so each 32-byte tile segment of an odd row is two HALF sectors —
+// partial-sector writes that cost the L2 a read-modify-write and a DRAM fill when they miss (638 vs 457 us for the same work into
+// an aligned layout, profiles/README.md).  HS removes most of them without giving up the locality of "one unit per CTA":
+//   * within a unit each group takes a RUN of consecutive column tiles (13 tiles: groups get tiles 0-3, 4-6, 7-9, 10-12) instead of
+//     every NGROUP-th one; the tiles are still issued round-robin over the groups, so the stage ring behaves exactly as before;
+//   * in an odd row, lanes c >= 4 of tile k hold the FIRST half of a sector whose second half belongs to lanes c < 4 of tile k + 1.
+//     Inside a run the same thread processes both tiles in program order, so tile k writes that whole sector in ONE store (data in
+//     the first half, zeros in the second) and tile k + 1 later overwrites its half — a 16-byte write into a sector that is already
+//     complete in the L2.  Only the sectors at run boundaries (3 of 12) and row ends are still written in two halves.
+template <int F, int R_LOG, bool PERM, int NSTAGE, int NGROUP, int GTHREADS, bool HS = false>
 __global__ void __launch_bounds__(NGROUP * GTHREADS + 32, 1) ntt_pass_pipe_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ PassArgs a) {
+    static_assert(!(HS && PERM), "the half-sector variant is the last (non-permuted) pass");
     constexpr u32 CT = 8;
     constexpr int Q2 = (R_LOG + 1) / 2, Q1 = R_LOG - Q2;
     constexpr u32 E1 = 1u << Q1, E2 = 1u << Q2, R = 1u << R_LOG;
@@ -509,6 +520,14 @@ __global__ void __launch_bounds__(NGROUP * GTHREADS + 32, 1) ntt_pass_pipe_kerne
         ct0 = chunk * a.tpi;
         ct1 = min(ct0 + a.tpi, a.n_ctiles);
     };
+    // HS: the i-th tile issued for a unit (i = 0 .. n - 1, owner group i % NGROUP) is column tile run_start(i % NGROUP) + i / NGROUP,
+    // where group g's run has n / NGROUP (+1 for g < n % NGROUP) tiles
+    auto run_tile = [&](u32 i, u32 n, u32 &run_pos, u32 &run_len) {
+        const u32 g = i % NGROUP, base = n / NGROUP, extra = n % NGROUP;
+        run_pos = i / NGROUP;
+        run_len = base + (g < extra ? 1u : 0u);
+        return g * base + min(g, extra) + run_pos;
+    };
 
     if (threadIdx.x >= NGROUP * GTHREADS) {
         // ---------------- producer ----------------
@@ -538,7 +557,9 @@ __global__ void __launch_bounds__(NGROUP * GTHREADS + 32, 1) ntt_pass_pipe_kerne
             const int blk_sh = PERM ? lowbits : a.l0;   // dim-4 coordinates per 2^log_n-row block
             const int c3 = PERM ? 0 : (int)L;
             const int c4 = (PERM ? (lowbits ? (int)(__brev(L) >> (32 - lowbits)) : 0) : (int)T) + (int)(in_block << blk_sh);
-            for (u32 ct = ct0; ct < ct1; ct++, q++) {
+            for (u32 cti = ct0; cti < ct1; cti++, q++) {
+                u32 rp_, rl_;
+                const u32 ct = HS ? ct0 + run_tile(cti - ct0, ct1 - ct0, rp_, rl_) : cti;
                 const u32 s = q % NSTAGE, k = q / NSTAGE;
                 mbar_wait(empty_bar(s), (k & 1u) ^ 1u);
                 mbar_expect_tx(full_bar(s), BOX_BYTES);
@@ -569,7 +590,9 @@ __global__ void __launch_bounds__(NGROUP * GTHREADS + 32, 1) ntt_pass_pipe_kerne
         const uint2 *tws = tws0 + b * R;
         const u32 ibase = (a.l0 == 0 ? 0u : (T << (a.log_n - a.l0))) | L;
         bool tw_ready = false;
-        for (u32 ct = ct0; ct < ct1; ct++, q++) {
+        for (u32 cti = ct0; cti < ct1; cti++, q++) {
+            u32 run_pos = 0, run_len = 0;
+            const u32 ct = HS ? ct0 + run_tile(cti - ct0, ct1 - ct0, run_pos, run_len) : cti;
             const u32 s = q % NSTAGE, k = q / NSTAGE;
             const u32 col = ct * CT, cw = min(CT, a.wc - col);
             u32 *data = stages + (size_t)s * STAGE_WORDS;
@@ -581,7 +604,7 @@ __global__ void __launch_bounds__(NGROUP * GTHREADS + 32, 1) ntt_pass_pipe_kerne
             // processed faster than HBM latency varies: corrupted arrival counts, i.e. hangs and mbarrier traps).
             mbar_wait(full_bar(s), k & 1u);
             if (!tw_ready) { mbar_wait(twfull_bar(b), ph); tw_ready = true; }
-            if (q % NGROUP != gid) {
+            if ((HS ? (cti - ct0) % NGROUP : q % NGROUP) != gid) {
                 mbar_arrive(empty_bar(s));
                 mbar_arrive(twempty_bar(b));
                 continue;
@@ -664,7 +687,22 @@ __global__ void __launch_bounds__(NGROUP * GTHREADS + 32, 1) ntt_pass_pipe_kerne
                         const u32 grow = (coset << a.log_n) + row0;
                         p = a.shard_out[grow >> a.shard_log_rows] + (size_t)(grow & ((1u << a.shard_log_rows) - 1u)) * ow + col + c;
                     }
-                    if (a.out_bitrev) {
+                    if (HS && cw == CT) {
+                        // dense natural-order rows, even rows sector aligned, odd rows 16 bytes in (the host checked the alignment).
+                        // fill_next: the next tile of this group's run exists and is full width, so the SAME thread will later write
+                        // the real data over the zeros (identical thread -> (row, column) mapping)
+                        const bool fill_next = run_pos + 1 < run_len && (ct + 2) * CT <= a.wc;
+                        const bool lo = c < 4;
+                        u32 *pb = p + (lo ? 8 : 0);
+#pragma unroll
+                        for (u32 m = 0; m < E2; m++) {
+                            if ((m & 1u) == 0) { p[m * sstride] = x[m]; }
+                            else {
+                                if (lo) p[m * sstride] = x[m];                                   // second half of a sector that is already complete
+                                if (!lo || fill_next) pb[m * sstride] = lo ? 0u : x[m];           // ONE full-sector store: lanes 4-7 data, lanes 0-3 zeros
+                            }
+                        }
+                    } else if (a.out_bitrev) {
 #pragma unroll
                         for (u32 m = 0; m < E2; m++) p[brev_const<Q2>(m) * sstride] = x[m];
                     } else {
@@ -684,180 +722,6 @@ __global__ void __launch_bounds__(NGROUP * GTHREADS + 32, 1) ntt_pass_pipe_kerne
             kk++;
 #endif
         }
-    }
-}
-
-// ---- last pass into a half-sector pitch: group-owned units + full-sector stores --------------------------------------------
-// The LDE's last pass writes the caller's dense layout.  With a row pitch of 16 mod 32 bytes (w = 100, 300: w % 8 == 4) every odd
-// row starts in the middle of a 32-byte sector, so each 32-byte tile segment of an odd row is two HALF sectors — partial-sector
-// writes that cost the L2 a read-modify-write and, when they miss, a DRAM fill (638 vs 457 us for the same work into an aligned
-// layout, profiles/README.md).  This variant of the pipelined kernel removes them:
-//   * each consumer group owns a whole (row tile, coset) unit and walks its column tiles in order (the CTA interleaves NGROUP units:
-//     tile sequence = (ct 0, unit 0..NGROUP-1), (ct 1, unit 0..NGROUP-1), ... so the stage ring is used exactly as before), with one
-//     twiddle buffer per group;
-//   * in an odd row, lanes c >= 4 of tile k hold the FIRST half of a sector whose second half belongs to lanes c < 4 of tile k + 1.
-//     The same thread processes both tiles in program order, so tile k writes that whole sector in ONE store instruction (real data
-//     in the first half, zeros in the second) and tile k + 1 later overwrites its half: a 16-byte write into a sector that is
-//     already complete in the L2.  Every sector is thus first touched by a full-sector write: no fills, no partial-write misses.
-// Non-permuted input (tiled layout), dense natural-order output only: exactly the last pass of lde_tiled_impl.
-template <int F, int R_LOG, int NSTAGE, int NGROUP, int GTHREADS>
-__global__ void __launch_bounds__(NGROUP * GTHREADS + 32, 1) ntt_pass_runs_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ PassArgs a) {
-    constexpr u32 CT = 8;
-    constexpr int Q2 = (R_LOG + 1) / 2, Q1 = R_LOG - Q2;
-    constexpr u32 E1 = 1u << Q1, E2 = 1u << Q2, R = 1u << R_LOG;
-    constexpr u32 GS = E2, NG = E1;
-    constexpr u32 gstride = (GS + 1) * CT;
-    constexpr u32 STAGE_WORDS = NG * gstride;
-    constexpr u32 BOX_BYTES = STAGE_WORDS * 4;
-    static_assert(BOX_BYTES % 128 == 0, "stage alignment");
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    u32 *stages = reinterpret_cast<u32 *>(smem_raw);
-    uint2 *tws0 = reinterpret_cast<uint2 *>(smem_raw + (size_t)NSTAGE * BOX_BYTES);
-    const u32 bar0 = (u32)__cvta_generic_to_shared(smem_raw + (size_t)NSTAGE * BOX_BYTES + (size_t)NGROUP * R * sizeof(uint2));
-    auto full_bar = [&](u32 s) { return bar0 + 8u * s; };
-    auto empty_bar = [&](u32 s) { return bar0 + 8u * (NSTAGE + s); };
-    auto twfull_bar = [&](u32 j) { return bar0 + 8u * (2 * NSTAGE + j); };
-    auto twempty_bar = [&](u32 j) { return bar0 + 8u * (2 * NSTAGE + NGROUP + j); };
-
-    if (threadIdx.x == 0) {
-        for (u32 s = 0; s < NSTAGE; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), NGROUP * GTHREADS); }
-        for (u32 j = 0; j < NGROUP; j++) { mbar_init(twfull_bar(j), 1); mbar_init(twempty_bar(j), GTHREADS); }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-
-    const int lowbits = a.log_n - a.l1;
-    auto decode = [&](u32 unit, u32 &coset, u32 &L, u32 &T) {
-        coset = unit % a.n_cosets;
-        const u32 tile = unit / a.n_cosets;
-        L = tile & ((1u << lowbits) - 1u);
-        T = tile >> lowbits;
-    };
-    const u32 n_super = (a.n_items + NGROUP - 1) / NGROUP;
-
-    if (threadIdx.x >= NGROUP * GTHREADS) {
-        // ---------------- producer ----------------
-        if ((threadIdx.x & 31u) != 0) return;
-        u32 q = 0, ui = 0;
-        for (u32 si = blockIdx.x; si < n_super; si += gridDim.x, ui++) {
-            const u32 nj = min((u32)NGROUP, a.n_items - si * NGROUP);
-            int c3[NGROUP], c4[NGROUP];
-            for (u32 j = 0; j < nj; j++) {
-                u32 coset, L, T;
-                decode(si * NGROUP + j, coset, L, T);
-                mbar_wait(twempty_bar(j), (ui & 1u) ^ 1u);      // group j is done with its previous unit's twiddles
-                const uint2 *tw = a.tw + (size_t)coset * a.tw_stride;
-                uint2 *tws = tws0 + j * R;
-                tws[1] = tw[((size_t)1 << a.l0) + T];
-                mbar_expect_tx(twfull_bar(j), 8u * (R - 2u));
-#pragma unroll 1
-                for (int lam = 1; lam < R_LOG; lam++) {
-                    const uint2 *src = tw + ((size_t)1 << (a.l0 + lam)) + ((size_t)T << lam);
-                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                                 ::"r"((u32)__cvta_generic_to_shared(tws + (1u << lam))), "l"(src), "r"(8u << lam), "r"(twfull_bar(j)) : "memory");
-                }
-                const u32 in_block = a.in_blocks > 1 ? coset : 0u;
-                c3[j] = (int)L;
-                c4[j] = (int)T + (int)(in_block << a.l0);
-            }
-            for (u32 ct = 0; ct < a.n_ctiles; ct++)
-                for (u32 j = 0; j < nj; j++, q++) {
-                    const u32 s = q % NSTAGE, k = q / NSTAGE;
-                    mbar_wait(empty_bar(s), (k & 1u) ^ 1u);
-                    mbar_expect_tx(full_bar(s), BOX_BYTES);
-                    const int cc4 = c4[j] + (int)((ct * a.in_blocks) << a.l0);
-                    asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
-                                 ::"r"((u32)__cvta_generic_to_shared(stages + (size_t)s * STAGE_WORDS)), "l"(reinterpret_cast<unsigned long long>(&tmap)),
-                                   "r"(0), "r"(0), "r"(0), "r"(c3[j]), "r"(cc4), "r"(full_bar(s)) : "memory");
-                }
-        }
-        return;
-    }
-
-    // ---------------- consumers ----------------
-    const u32 gid = threadIdx.x / GTHREADS, tg = threadIdx.x - gid * GTHREADS;
-    const u32 ow = a.w;
-    const bool half_sector = a.half_sector != 0;
-    u32 q = 0, ui = 0;
-    for (u32 si = blockIdx.x; si < n_super; si += gridDim.x, ui++) {
-        const u32 nj = min((u32)NGROUP, a.n_items - si * NGROUP);
-        u32 coset = 0, L = 0, T = 0;
-        if (gid < nj) decode(si * NGROUP + gid, coset, L, T);
-        const uint2 *tws = tws0 + gid * R;
-        const u32 ibase = (a.l0 == 0 ? 0u : (T << (a.log_n - a.l0))) | L;
-        bool tw_ready = false;
-        for (u32 ct = 0; ct < a.n_ctiles; ct++)
-            for (u32 j = 0; j < nj; j++, q++) {
-                const u32 s = q % NSTAGE, k = q / NSTAGE;
-                mbar_wait(full_bar(s), k & 1u);                 // every group observes every stage phase (see ntt_pass_pipe_kernel)
-                if (j != gid) { mbar_arrive(empty_bar(s)); continue; }
-                if (!tw_ready) { mbar_wait(twfull_bar(gid), ui & 1u); tw_ready = true; }
-                const u32 col = ct * CT, cw = min(CT, a.wc - col);
-                u32 *data = stages + (size_t)s * STAGE_WORDS;
-                const u32 dg = GTHREADS / cw, dc = GTHREADS - dg * cw;
-                {   // ---- step 1 (in place): E1 values per item, Q1 layers
-                    u32 g = tg / cw, c = tg - g * cw;
-                    for (; g < E2; ) {
-                        u32 x[E1];
-                        u32 *sp = data + g * CT + c;
-#pragma unroll
-                        for (u32 m = 0; m < E1; m++) x[m] = sp[m * gstride];
-                        reg_network<F, Q1>(x, tws, 1u);
-#pragma unroll
-                        for (u32 m = 0; m < E1; m++) sp[m * gstride] = x[m];
-                        c += dc; g += dg;
-                        if (c >= cw) { c -= cw; g++; }
-                    }
-                }
-                asm volatile("bar.sync %0, %1;" ::"r"(gid + 1u), "r"((u32)GTHREADS) : "memory");
-                {   // ---- step 2: E2 values per item, Q2 layers, results straight to global memory (rows of a tile are contiguous)
-                    u32 *out = a.out + (size_t)coset * a.out_stride + col;
-                    // zero-filling the next tile's half sector is only sound when the SAME thread later writes the real data there:
-                    // this tile and the next are both full-width (identical thread -> (row, column) mapping)
-                    const bool fill_next = half_sector && cw == CT && (ct + 2) * CT <= a.wc;
-                    u32 g = tg / cw, c = tg - g * cw;
-                    bool released = false;
-                    for (; g < E1; ) {
-                        u32 x[E2];
-                        const u32 *sp = data + g * gstride + c;
-#pragma unroll
-                        for (u32 m = 0; m < E2; m++) x[m] = sp[m * CT];
-                        u32 gn = g + dg, cn = c + dc;
-                        if (cn >= cw) { cn -= cw; gn++; }
-                        if (gn >= E1) {
-                            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                            mbar_arrive(empty_bar(s));
-                            released = true;
-                        }
-                        reg_network<F, Q2>(x, tws, E1 + g);
-#pragma unroll
-                        for (u32 m = 0; m < E2; m++) x[m] = fp_reduce<F>(x[m]);
-                        const u32 row0 = ibase | (g << Q2);                       // lowbits == 0: the tile's rows are consecutive
-                        u32 *p = out + (size_t)row0 * ow + c;
-                        if (!half_sector || cw != CT) {
-#pragma unroll
-                            for (u32 m = 0; m < E2; m++) p[(size_t)m * ow] = x[m];
-                        } else {
-                            const bool lo = c < 4;                                  // even rows are sector aligned, odd rows start 16 bytes in
-                            u32 *pb = p + (lo ? 8 : 0);
-#pragma unroll
-                            for (u32 m = 0; m < E2; m++) {
-                                if ((m & 1u) == 0) { p[(size_t)m * ow] = x[m]; }
-                                else {
-                                    if (lo) p[(size_t)m * ow] = x[m];             // second half of a sector that is already complete
-                                    if (!lo || fill_next) pb[(size_t)m * ow] = lo ? 0u : x[m];   // one full-sector store: lanes 4-7 data, lanes 0-3 zeros
-                                }
-                            }
-                        }
-                        g = gn; c = cn;
-                    }
-                    if (!released) {
-                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                        mbar_arrive(empty_bar(s));
-                    }
-                }
-            }
-        if (gid < nj) mbar_arrive(twempty_bar(gid));
     }
 }
 
@@ -1081,7 +945,7 @@ static bool pipe_eligible(const PassArgs &a) {
     return true;
 }
 
-template <int F, int R_LOG, bool PERM>
+template <int F, int R_LOG, bool PERM, bool HS = false>
 static int32_t launch_pipe_r(p3gpu_ctx *ctx, PassArgs a) {
     constexpr int NSTAGE = 6, NGROUP = 4, GTHREADS = 128;
     constexpr int Q2 = (R_LOG + 1) / 2, Q1 = R_LOG - Q2;
@@ -1104,7 +968,7 @@ static int32_t launch_pipe_r(p3gpu_ctx *ctx, PassArgs a) {
     P3_CHECK(items < (1ull << 31), P3GPU_EINVAL, "ntt: too many tiles");
     P3_CHECK((size_t)a.tpi * NGROUP * GTHREADS < (1u << 20), P3GPU_EINVAL, "ntt: too many column tiles per unit for the mbarrier count");
     a.n_items = (u32)items;
-    auto kern = ntt_pass_pipe_kernel<F, R_LOG, PERM, NSTAGE, NGROUP, GTHREADS>;
+    auto kern = ntt_pass_pipe_kernel<F, R_LOG, PERM, NSTAGE, NGROUP, GTHREADS, HS>;
     static bool attr_set[64] = {false};
     if (!attr_set[ctx->device & 63]) {
         P3_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1118,6 +982,8 @@ static int32_t launch_pipe_r(p3gpu_ctx *ctx, PassArgs a) {
 }
 template <int F, int R_LOG>
 static int32_t launch_pipe_p(p3gpu_ctx *ctx, const PassArgs &a) {
+    if (a.half_sector && !a.in_bitrev && !a.out_bitrev && !a.out_tiled && a.out_sh == 0 && a.out_add == 0 && a.shard_log_rows == 0 && a.l1 == a.log_n)
+        return launch_pipe_r<F, R_LOG, false, true>(ctx, a);
     return a.in_bitrev ? launch_pipe_r<F, R_LOG, true>(ctx, a) : launch_pipe_r<F, R_LOG, false>(ctx, a);
 }
 template <int F>
@@ -1128,60 +994,6 @@ static int32_t launch_pipe(p3gpu_ctx *ctx, const PassArgs &a) {
         case 8: return launch_pipe_p<F, 8>(ctx, a);
         case 9: return launch_pipe_p<F, 9>(ctx, a);
         default: return launch_pipe_p<F, 10>(ctx, a);
-    }
-}
-
-// Last pass of the tiled LDE into the caller's dense layout with group-owned units (ntt_pass_runs_kernel).
-template <int F, int R_LOG>
-static int32_t launch_runs_r(p3gpu_ctx *ctx, PassArgs a) {
-    constexpr int NSTAGE = 5, NGROUP = 4, GTHREADS = 128;
-    constexpr int Q2 = (R_LOG + 1) / 2, Q1 = R_LOG - Q2;
-    constexpr size_t box_bytes = ((size_t)1 << Q1) * (((size_t)1 << Q2) + 1) * 8 * 4;
-    constexpr size_t smem = NSTAGE * box_bytes + NGROUP * ((size_t)1 << R_LOG) * sizeof(uint2) + (2 * NSTAGE + 2 * NGROUP) * 8;
-    static_assert(smem <= 227 * 1024, "runs NTT kernel: shared memory budget");
-    CUtensorMap tm;
-    if (a.wc == 0) a.wc = a.w;
-    if (a.in_blocks == 0) a.in_blocks = 1;
-    P3_TRY(make_pass_tensor_map(a, false, &tm));
-    a.n_ctiles = (a.wc + 7) / 8;
-    a.csplit = 1; a.tpi = a.n_ctiles;
-    const size_t units = ((size_t)1 << (a.log_n - R_LOG)) * a.n_cosets;
-    P3_CHECK(units < (1ull << 31), P3GPU_EINVAL, "ntt: too many tiles");
-    a.n_items = (u32)units;
-    auto kern = ntt_pass_runs_kernel<F, R_LOG, NSTAGE, NGROUP, GTHREADS>;
-    static bool attr_set[64] = {false};
-    if (!attr_set[ctx->device & 63]) {
-        P3_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set[ctx->device & 63] = true;
-    }
-    const size_t n_super = (units + NGROUP - 1) / NGROUP;
-    const size_t grid = std::min(n_super, (size_t)ctx->sm_count);
-    kern<<<(unsigned)grid, NGROUP * GTHREADS + 32, smem, ctx->stream>>>(tm, a);
-    ctx->launches++;
-    P3_CUDA(cudaGetLastError());
-    return P3GPU_OK;
-}
-// the kernel pays off when the pitch leaves odd rows half a sector off (w % 8 == 4) and there are enough units to give every
-// group of every SM its own; P3GPU_NTT_RUNS=0 switches it off, =2 forces it for aligned pitches too (tests)
-static bool runs_eligible(p3gpu_ctx *ctx, const PassArgs &a, size_t out_pitch) {
-    const int mode = env_int("P3GPU_NTT_RUNS", 1);
-    if (mode == 0 || a.in_tiled == 0 || a.out_tiled || a.out_bitrev || a.out_sh || a.out_add || a.shard_log_rows || a.has_scale) return false;
-    if (a.log_n != a.l1 || !a.final_reduce) return false;
-    const int r = a.l1 - a.l0;
-    if (r < 6 || r > 10) return false;
-    const size_t units = ((size_t)1 << (a.log_n - r)) * a.n_cosets;
-    if (mode == 2) return true;
-    if (units < 8 * (size_t)ctx->sm_count) return false;
-    return out_pitch % 8 == 4 && reinterpret_cast<uintptr_t>(a.out) % 32 == 0;
-}
-template <int F>
-static int32_t launch_runs(p3gpu_ctx *ctx, const PassArgs &a) {
-    switch (a.l1 - a.l0) {
-        case 6: return launch_runs_r<F, 6>(ctx, a);
-        case 7: return launch_runs_r<F, 7>(ctx, a);
-        case 8: return launch_runs_r<F, 8>(ctx, a);
-        case 9: return launch_runs_r<F, 9>(ctx, a);
-        default: return launch_runs_r<F, 10>(ctx, a);
     }
 }
 
@@ -1415,11 +1227,10 @@ static int32_t lde_tiled_impl(p3gpu_ctx *ctx, const u32 *d_in, size_t h, size_t 
             }
             else if (k == plan.n_passes - 1) { a.out = d_out + col0; a.out_tiled = 0; a.out_stride = h * out_pitch; a.final_reduce = 1; }
             else { a.out = (u32 *)B; a.out_tiled = 1; }
-            if (k == plan.n_passes - 1 && !shard && runs_eligible(ctx, a, out_pitch)) {
-                a.half_sector = (out_pitch % 8 == 4 && reinterpret_cast<uintptr_t>(a.out) % 32 == 0 && (h * out_pitch) % 8 == 0) ? 1u : 0u;
-                P3_TRY(launch_runs<F>(ctx, a));
-                continue;
-            }
+            // half-sector pitch (w % 8 == 4): column-tile runs per group + full-sector stores in the last pass (see the kernel)
+            if (k == plan.n_passes - 1 && !shard && env_int("P3GPU_NTT_HALFSECTOR", 1) && out_pitch % 8 == 4 &&
+                reinterpret_cast<uintptr_t>(a.out) % 32 == 0 && (h * out_pitch) % 8 == 0)
+                a.half_sector = 1;
             P3_TRY(launch_pipe<F>(ctx, a));
         }
     }
