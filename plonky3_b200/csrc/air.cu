@@ -36,47 +36,69 @@ template <int F> __device__ __forceinline__ void air_internal_layer(u32 (&s)[AIR
     DiagLoop<F, AIR_W, 1>::run(s, sum);
 }
 
-// ---- trace generation: one thread per permutation ------------------------------------------------------------------
+// ---- trace generation: one thread per permutation, rows written through a per-warp shared-memory transpose ------------------
+// A thread produces its permutation's 164 columns 16 (or rounds_p) at a time.  Written straight from the thread, a warp's store
+// instruction touches 32 different rows 16 bytes each — partial sectors, and ncu shows the kernel stuck on the store queue
+// (lg_throttle 34, 1.5 Gperm/s).  Instead every group of n values per permutation goes through a [32][n + 1] tile per warp and is
+// written back with consecutive lanes on consecutive words of a row: whole 64/80-byte row segments per instruction.
 template <int F>
 __global__ void __launch_bounds__(128) p2air_generate_kernel(const u32 *inputs, size_t n_perms, u32 *trace, const __grid_constant__ AirConsts k) {
-    const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= n_perms) return;
+    __shared__ u32 tiles[4][32 * 33];
+    u32 *tile = tiles[threadIdx.x >> 5];
+    const unsigned lane = threadIdx.x & 31u;
+    const size_t p0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) - lane;       // first permutation of this warp
+    if (p0 >= n_perms) return;
+    const size_t p = p0 + lane;
+    const bool live = p < n_perms;
     const size_t cols = 144 + (size_t)k.rounds_p;
-    u32 s[AIR_W];
-    const uint4 *ip = reinterpret_cast<const uint4 *>(inputs + p * 16);
-#pragma unroll
-    for (int i = 0; i < 4; i++) { const uint4 v = __ldg(ip + i); s[4 * i] = v.x; s[4 * i + 1] = v.y; s[4 * i + 2] = v.z; s[4 * i + 3] = v.w; }
-    u32 *row = trace + p * cols;
-    auto put16 = [&](u32 *dst) {
-        if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
-#pragma unroll
-            for (int i = 0; i < 4; i++) reinterpret_cast<uint4 *>(dst)[i] = make_uint4(s[4 * i], s[4 * i + 1], s[4 * i + 2], s[4 * i + 3]);
-        } else {
-#pragma unroll
-            for (int i = 0; i < 16; i++) dst[i] = s[i];
+    const unsigned n_warp = (unsigned)min((size_t)32, n_perms - p0);
+    // write `n` values per permutation (held as tile[perm * (n + 1) + i]) to columns [off, off + n) of the warp's rows
+    auto flush = [&](unsigned n, size_t off) {
+        __syncwarp();
+        for (unsigned idx = lane; idx < n_warp * n; idx += 32) {
+            const unsigned perm = idx / n, i = idx - perm * n;
+            trace[(p0 + perm) * cols + off + i] = tile[perm * (n + 1) + i];
         }
+        __syncwarp();
     };
-    put16(row); row += 16;
+    u32 s[AIR_W];
+    if (live) {
+        const uint4 *ip = reinterpret_cast<const uint4 *>(inputs + p * 16);
+#pragma unroll
+        for (int i = 0; i < 4; i++) { const uint4 v = __ldg(ip + i); s[4 * i] = v.x; s[4 * i + 1] = v.y; s[4 * i + 2] = v.z; s[4 * i + 3] = v.w; }
+    } else {
+#pragma unroll
+        for (int i = 0; i < AIR_W; i++) s[i] = 0;
+    }
+    auto put16 = [&](size_t off) {
+#pragma unroll
+        for (int i = 0; i < AIR_W; i++) tile[lane * 17 + i] = s[i];
+        flush(16, off);
+    };
+    size_t off = 0;
+    put16(off); off += 16;
     mds_light<F, AIR_W>(s);
 #pragma unroll 1
     for (int r = 0; r < 4; r++) {
 #pragma unroll
         for (int i = 0; i < AIR_W; i++) s[i] = sbox<F>(fp_add<F>(s[i], k.beg[r * 16 + i]));
         mds_light<F, AIR_W>(s);
-        put16(row); row += 16;
+        put16(off); off += 16;
     }
+    const unsigned rp = (unsigned)k.rounds_p;
 #pragma unroll 1
-    for (int r = 0; r < k.rounds_p; r++) {
+    for (unsigned r = 0; r < rp; r++) {
         s[0] = sbox<F>(fp_add<F>(s[0], k.part[r]));
-        *row++ = s[0];
+        tile[lane * (rp + 1) + r] = s[0];
         air_internal_layer<F>(s);
     }
+    flush(rp, off); off += rp;
 #pragma unroll 1
     for (int r = 0; r < 4; r++) {
 #pragma unroll
         for (int i = 0; i < AIR_W; i++) s[i] = sbox<F>(fp_add<F>(s[i], k.end[r * 16 + i]));
         mds_light<F, AIR_W>(s);
-        put16(row); row += 16;
+        put16(off); off += 16;
     }
 }
 
@@ -105,9 +127,15 @@ struct QuotArgs {
 
 template <int F>
 __global__ void __launch_bounds__(128) p2air_quotient_kernel(const QuotArgs a, const __grid_constant__ AirConsts k) {
-    extern __shared__ uint4 ap[];                                   // alpha powers
+    // alpha powers, one padded row per permutation of the vector: constraint kk of permutation v (global index j = v * nc + kk,
+    // multiplied by alpha^(n_all - 1 - j)) sits at ap[v * (nc + 1) + kk].  The row stride of nc + 1 = 149 entries (596 words = 20
+    // mod 32 banks) spreads the 8 permutations a warp works on over disjoint banks; without the pad they collide 4 ways (ncu).
+    extern __shared__ uint4 ap[];
     const int nc = 128 + k.rounds_p, n_all = nc * a.vec_len;
-    for (int t = threadIdx.x; t < n_all; t += blockDim.x) ap[t] = __ldg(reinterpret_cast<const uint4 *>(a.apow) + t);
+    for (int t = threadIdx.x; t < n_all; t += blockDim.x) {
+        const int j = n_all - 1 - t;
+        ap[(j / nc) * (nc + 1) + (j % nc)] = __ldg(reinterpret_cast<const uint4 *>(a.apow) + t);
+    }
     __syncthreads();
     const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int lanes = a.vec_len;                                    // power of two <= 32 (checked by the host)
@@ -119,8 +147,7 @@ __global__ void __launch_bounds__(128) p2air_quotient_kernel(const QuotArgs a, c
         const size_t cols = 144 + (size_t)k.rounds_p;
         const size_t m = (size_t)(__brevll((unsigned long long)i) >> (64 - a.log_h));
         const u32 *c = a.lde + (m * lanes + v) * cols;
-        // constraint j = v * nc + kk uses alpha^(n_all - 1 - j): walk the table downwards
-        const uint4 *apv = ap + (n_all - 1 - v * nc);
+        const uint4 *apv = ap + v * (nc + 1);
         // a permutation's 164 columns start 16-byte aligned (656 = 41 x 16 bytes): 16-byte loads throughout
         const uint4 *c4 = reinterpret_cast<const uint4 *>(c);
         u32 s[AIR_W];
@@ -139,8 +166,8 @@ __global__ void __launch_bounds__(128) p2air_quotient_kernel(const QuotArgs a, c
             u32 post[AIR_W];
             ld16(post);
 #pragma unroll
-            for (int x = 0; x < AIR_W; x++) { qmac<F>(acc, fp_sub<F>(s[x], post[x]), apv[-x]); s[x] = post[x]; }
-            apv -= 16;
+            for (int x = 0; x < AIR_W; x++) { qmac<F>(acc, fp_sub<F>(s[x], post[x]), apv[x]); s[x] = post[x]; }
+            apv += 16;
         }
         {
             const u32 *cp = reinterpret_cast<const u32 *>(c4);
@@ -151,7 +178,7 @@ __global__ void __launch_bounds__(128) p2air_quotient_kernel(const QuotArgs a, c
 #pragma unroll
                 for (int t2 = 0; t2 < 4; t2++) {
                     const u32 x3 = sbox<F>(fp_add<F>(s[0], k.part[r + t2]));
-                    qmac<F>(acc, fp_sub<F>(x3, pv[t2]), *apv--);
+                    qmac<F>(acc, fp_sub<F>(x3, pv[t2]), *apv++);
                     s[0] = pv[t2];
                     air_internal_layer<F>(s);
                 }
@@ -166,8 +193,8 @@ __global__ void __launch_bounds__(128) p2air_quotient_kernel(const QuotArgs a, c
             u32 post[AIR_W];
             ld16(post);
 #pragma unroll
-            for (int x = 0; x < AIR_W; x++) { qmac<F>(acc, fp_sub<F>(s[x], post[x]), apv[-x]); s[x] = post[x]; }
-            apv -= 16;
+            for (int x = 0; x < AIR_W; x++) { qmac<F>(acc, fp_sub<F>(s[x], post[x]), apv[x]); s[x] = post[x]; }
+            apv += 16;
         }
     }
     u32 r[4];
@@ -254,7 +281,7 @@ int32_t air_quotient(p3gpu_ctx *ctx, int field, int vec_len, const u32 *d_lde, u
     QuotArgs qa;
     qa.lde = d_lde; qa.q = d_q; qa.apow = apow; qa.invz = invz; qa.log_h = log_h; qa.rate_mask = (unsigned)(nz - 1); qa.vec_len = vec_len;
     const size_t threads = ((size_t)1 << log_h) * vec_len;
-    const size_t smem = (size_t)n_all * 16;
+    const size_t smem = (size_t)vec_len * (nc + 1) * 16;
     auto kern = p2air_quotient_kernel<F>;
     if (smem > 48 * 1024) P3_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<(unsigned)((threads + 127) / 128), 128, smem, ctx->stream>>>(qa, *k);

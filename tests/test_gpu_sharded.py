@@ -36,12 +36,12 @@ def _gpus(n):
     return out
 
 
-@pytest.mark.parametrize("mode", ["staged", "fused"])
+@pytest.mark.parametrize("mode", ["dma", "staged", "fused"])
 @pytest.mark.parametrize("f,log_h,w,world", [(KoalaBear, 12, 100, 2), (BabyBear, 13, 72, 4), (KoalaBear, 14, 328, 8), (KoalaBear, 15, 200, 2)])
 def test_sharded_lde_scatters_row_blocks(f, log_h, w, world, mode, monkeypatch):
     """Every rank's column-block LDE lands in the right rows/columns of every rank's row block — both exchange variants:
     `staged` (column chunks into a staging buffer + coalesced push kernel on a second stream) and `fused` (the last pass of the
-    transform stores its tiles straight into the owners' row blocks)."""
+    transform stores its tiles straight into the owners' row blocks); `dma` (default) = staged with 2-D peer copies."""
     monkeypatch.setenv("P3GPU_SHARD_MODE", mode)
     gpus = _gpus(world)
     H = 2 << log_h
