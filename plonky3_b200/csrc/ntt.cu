@@ -83,7 +83,6 @@ struct PassArgs {
     // column blocks into row blocks happens in the pass's own stores, tile by tile, over NVLink.
     u32 *shard_out[16];
     int shard_log_rows;   // 0 = off
-    u32 half_sector;      // last pass, dense output pitch = 16 mod 32 bytes, 32-byte aligned base: HS variant of the pipelined kernel
 };
 
 template <int LOG_CT> __device__ __forceinline__ u32 sidx(u32 row, u32 c) {
@@ -471,22 +470,8 @@ __device__ __forceinline__ void mbar_arrive(u32 bar) { asm volatile("mbarrier.ar
 __device__ __forceinline__ void mbar_arrive_n(u32 bar, u32 n) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(n) : "memory"); }
 __device__ __forceinline__ void mbar_expect_tx(u32 bar, u32 bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory"); }
 
-// HS (half-sector variant; last LDE pass only: dense natural-order output whose row pitch is 16 mod 32 bytes, w % 8 == 4, e.g. w = 100
-// or 300).  Every odd row then starts in the middle of a 32-byte sector and each 32-byte tile segment of an odd row is two HALF
-// sectors.  A pitch sweep under ncu (profiles/r02_lde_pitch_sweep.txt) isolates the cost: the last pass takes 4.65 us per column for
-// w = 96 / 104 / 128 and 6.35 us for w = 100 (+189 MB DRAM reads, issue 56 % instead of 68 %).  HS writes every such sector ONCE,
-// whole:
-//   * within a unit each group takes a RUN of consecutive column tiles (13 tiles: 0-3, 4-6, 7-9, 10-12) instead of every NGROUP-th
-//     one; tiles are still issued round-robin over the groups, so the stage ring behaves exactly as before and all groups stay on
-//     the same rows (the L2 locality of "one unit per CTA" is kept — a variant with one unit per group was 47 % slower);
-//   * in an odd row, lanes c >= 4 of tile k hold the first half of a sector whose second half belongs to lanes c < 4 of tile k + 1.
-//     Lanes c >= 4 park their odd-row results in a per-group shared-memory carry buffer instead of storing them; at tile k + 1 the
-//     same thread (identical thread -> (row, column) mapping) stores the parked values 32 bytes to the left in the SAME store
-//     instruction in which lanes c < 4 store their own: eight lanes, one complete sector.  Only the first and last tile of a run
-//     still write half sectors (8 of 26 per odd row for w = 100).
-template <int F, int R_LOG, bool PERM, int NSTAGE, int NGROUP, int GTHREADS, bool HS = false>
+template <int F, int R_LOG, bool PERM, int NSTAGE, int NGROUP, int GTHREADS>
 __global__ void __launch_bounds__(NGROUP * GTHREADS + 32, 1) ntt_pass_pipe_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ PassArgs a) {
-    static_assert(!(HS && PERM), "the half-sector variant is the last (non-permuted) pass");
     constexpr u32 CT = 8;
     constexpr int Q2 = (R_LOG + 1) / 2, Q1 = R_LOG - Q2;
     constexpr u32 E1 = 1u << Q1, E2 = 1u << Q2, R = 1u << R_LOG;
@@ -504,9 +489,6 @@ __global__ void __launch_bounds__(NGROUP * GTHREADS + 32, 1) ntt_pass_pipe_kerne
     auto empty_bar = [&](u32 s) { return bar0 + 8u * (NSTAGE + s); };
     auto twfull_bar = [&](u32 b) { return bar0 + 8u * (2 * NSTAGE + b); };
     auto twempty_bar = [&](u32 b) { return bar0 + 8u * (2 * NSTAGE + 2 + b); };
-    // HS: carry buffers behind the barriers, one per consumer group: (E1 * 4) items x (E2 / 2 odd rows + 1 pad) words
-    constexpr u32 CARRY_WORDS = (1u << Q1) * 4u * ((1u << Q2) / 2u + 1u);
-    u32 *carry0 = reinterpret_cast<u32 *>(smem_raw + (size_t)NSTAGE * BOX_BYTES + 2 * R * sizeof(uint2) + (2 * NSTAGE + 4) * 8);
 
     if (threadIdx.x == 0) {
         for (u32 s = 0; s < NSTAGE; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), NGROUP * GTHREADS); }
@@ -525,14 +507,6 @@ __global__ void __launch_bounds__(NGROUP * GTHREADS + 32, 1) ntt_pass_pipe_kerne
         T = tile >> lowbits;
         ct0 = chunk * a.tpi;
         ct1 = min(ct0 + a.tpi, a.n_ctiles);
-    };
-    // HS: the i-th tile issued for a unit (i = 0 .. n - 1, owner group i % NGROUP) is column tile run_start(i % NGROUP) + i / NGROUP,
-    // where group g's run has n / NGROUP (+1 for g < n % NGROUP) tiles
-    auto run_tile = [&](u32 i, u32 n, u32 &run_pos, u32 &run_len) {
-        const u32 g = i % NGROUP, base = n / NGROUP, extra = n % NGROUP;
-        run_pos = i / NGROUP;
-        run_len = base + (g < extra ? 1u : 0u);
-        return g * base + min(g, extra) + run_pos;
     };
 
     if (threadIdx.x >= NGROUP * GTHREADS) {
@@ -563,9 +537,7 @@ __global__ void __launch_bounds__(NGROUP * GTHREADS + 32, 1) ntt_pass_pipe_kerne
             const int blk_sh = PERM ? lowbits : a.l0;   // dim-4 coordinates per 2^log_n-row block
             const int c3 = PERM ? 0 : (int)L;
             const int c4 = (PERM ? (lowbits ? (int)(__brev(L) >> (32 - lowbits)) : 0) : (int)T) + (int)(in_block << blk_sh);
-            for (u32 cti = ct0; cti < ct1; cti++, q++) {
-                u32 rp_, rl_;
-                const u32 ct = HS ? ct0 + run_tile(cti - ct0, ct1 - ct0, rp_, rl_) : cti;
+            for (u32 ct = ct0; ct < ct1; ct++, q++) {
                 const u32 s = q % NSTAGE, k = q / NSTAGE;
                 mbar_wait(empty_bar(s), (k & 1u) ^ 1u);
                 mbar_expect_tx(full_bar(s), BOX_BYTES);
@@ -596,9 +568,7 @@ __global__ void __launch_bounds__(NGROUP * GTHREADS + 32, 1) ntt_pass_pipe_kerne
         const uint2 *tws = tws0 + b * R;
         const u32 ibase = (a.l0 == 0 ? 0u : (T << (a.log_n - a.l0))) | L;
         bool tw_ready = false;
-        for (u32 cti = ct0; cti < ct1; cti++, q++) {
-            u32 run_pos = 0, run_len = 0;
-            const u32 ct = HS ? ct0 + run_tile(cti - ct0, ct1 - ct0, run_pos, run_len) : cti;
+        for (u32 ct = ct0; ct < ct1; ct++, q++) {
             const u32 s = q % NSTAGE, k = q / NSTAGE;
             const u32 col = ct * CT, cw = min(CT, a.wc - col);
             u32 *data = stages + (size_t)s * STAGE_WORDS;
@@ -610,7 +580,7 @@ __global__ void __launch_bounds__(NGROUP * GTHREADS + 32, 1) ntt_pass_pipe_kerne
             // processed faster than HBM latency varies: corrupted arrival counts, i.e. hangs and mbarrier traps).
             mbar_wait(full_bar(s), k & 1u);
             if (!tw_ready) { mbar_wait(twfull_bar(b), ph); tw_ready = true; }
-            if ((HS ? (cti - ct0) % NGROUP : q % NGROUP) != gid) {
+            if (q % NGROUP != gid) {
                 mbar_arrive(empty_bar(s));
                 mbar_arrive(twempty_bar(b));
                 continue;
@@ -693,21 +663,7 @@ __global__ void __launch_bounds__(NGROUP * GTHREADS + 32, 1) ntt_pass_pipe_kerne
                         const u32 grow = (coset << a.log_n) + row0;
                         p = a.shard_out[grow >> a.shard_log_rows] + (size_t)(grow & ((1u << a.shard_log_rows) - 1u)) * ow + col + c;
                     }
-                    if (HS && cw == CT) {
-                        // dense natural-order rows; even rows are sector aligned, odd rows start 16 bytes in (alignment checked by the host)
-                        const bool hi = c >= 4;
-                        const bool have_prev = run_pos > 0;                                        // the previous tile of my run parked its values
-                        const bool park = run_pos + 1 < run_len && (ct + 2) * CT <= a.wc;          // the next tile of my run is full width: it stores for me
-                        u32 *cs = carry0 + gid * CARRY_WORDS + (g * 4u + (c & 3u)) * (E2 / 2u + 1u);
-#pragma unroll
-                        for (u32 m = 0; m < E2; m++) {
-                            if ((m & 1u) == 0) { p[m * sstride] = x[m]; continue; }
-                            // one store instruction per odd row: lanes 0-3 their own words, lanes 4-7 the parked words of the tile to the left
-                            const u32 v = hi ? cs[m >> 1] : x[m];
-                            if (!hi || have_prev) p[m * sstride - (hi ? 8 : 0)] = v;
-                            if (hi) { if (park) cs[m >> 1] = x[m]; else p[m * sstride] = x[m]; }
-                        }
-                    } else if (a.out_bitrev) {
+                    if (a.out_bitrev) {
 #pragma unroll
                         for (u32 m = 0; m < E2; m++) p[brev_const<Q2>(m) * sstride] = x[m];
                     } else {
@@ -950,14 +906,13 @@ static bool pipe_eligible(const PassArgs &a) {
     return true;
 }
 
-template <int F, int R_LOG, bool PERM, bool HS = false>
+template <int F, int R_LOG, bool PERM>
 static int32_t launch_pipe_r(p3gpu_ctx *ctx, PassArgs a) {
-    constexpr int NSTAGE = HS ? 5 : 6, NGROUP = 4, GTHREADS = 128;
+    constexpr int NSTAGE = 6, NGROUP = 4, GTHREADS = 128;
     constexpr int Q2 = (R_LOG + 1) / 2, Q1 = R_LOG - Q2;
     constexpr size_t GS = PERM ? (1u << Q1) : (1u << Q2), NG = PERM ? (1u << Q2) : (1u << Q1);
     constexpr size_t box_bytes = NG * (GS + 1) * 8 * 4;
-    constexpr size_t carry = HS ? (size_t)NGROUP * (((size_t)1 << Q1) * 4 * (((size_t)1 << Q2) / 2 + 1)) * 4 : 0;
-    constexpr size_t smem = NSTAGE * box_bytes + 2 * ((size_t)1 << R_LOG) * sizeof(uint2) + (2 * NSTAGE + 4) * 8 + carry;
+    constexpr size_t smem = NSTAGE * box_bytes + 2 * ((size_t)1 << R_LOG) * sizeof(uint2) + (2 * NSTAGE + 4) * 8;
     static_assert(smem <= 227 * 1024, "pipelined NTT kernel: shared memory budget");
     CUtensorMap tm;
     if (a.wc == 0) a.wc = a.w;
@@ -974,7 +929,7 @@ static int32_t launch_pipe_r(p3gpu_ctx *ctx, PassArgs a) {
     P3_CHECK(items < (1ull << 31), P3GPU_EINVAL, "ntt: too many tiles");
     P3_CHECK((size_t)a.tpi * NGROUP * GTHREADS < (1u << 20), P3GPU_EINVAL, "ntt: too many column tiles per unit for the mbarrier count");
     a.n_items = (u32)items;
-    auto kern = ntt_pass_pipe_kernel<F, R_LOG, PERM, NSTAGE, NGROUP, GTHREADS, HS>;
+    auto kern = ntt_pass_pipe_kernel<F, R_LOG, PERM, NSTAGE, NGROUP, GTHREADS>;
     static bool attr_set[64] = {false};
     if (!attr_set[ctx->device & 63]) {
         P3_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -988,8 +943,6 @@ static int32_t launch_pipe_r(p3gpu_ctx *ctx, PassArgs a) {
 }
 template <int F, int R_LOG>
 static int32_t launch_pipe_p(p3gpu_ctx *ctx, const PassArgs &a) {
-    if (a.half_sector && !a.in_bitrev && !a.out_bitrev && !a.out_tiled && a.out_sh == 0 && a.out_add == 0 && a.shard_log_rows == 0 && a.l1 == a.log_n)
-        return launch_pipe_r<F, R_LOG, false, true>(ctx, a);
     return a.in_bitrev ? launch_pipe_r<F, R_LOG, true>(ctx, a) : launch_pipe_r<F, R_LOG, false>(ctx, a);
 }
 template <int F>
@@ -1233,9 +1186,6 @@ static int32_t lde_tiled_impl(p3gpu_ctx *ctx, const u32 *d_in, size_t h, size_t 
             }
             else if (k == plan.n_passes - 1) { a.out = d_out + col0; a.out_tiled = 0; a.out_stride = h * out_pitch; a.final_reduce = 1; }
             else { a.out = (u32 *)B; a.out_tiled = 1; }
-            if (k == plan.n_passes - 1 && !shard && env_int("P3GPU_NTT_HALFSECTOR", 1) && out_pitch % 8 == 4 &&
-                reinterpret_cast<uintptr_t>(a.out) % 32 == 0 && (h * out_pitch) % 8 == 0)
-                a.half_sector = 1;
             P3_TRY(launch_pipe<F>(ctx, a));
         }
     }

@@ -628,27 +628,3 @@ def test_batch_stark_fixture_main_commitment_on_gpu(gpu):
         cap = batch_fixture_main_cap(lambda m, bits, s: dft.coset_lde_batch(to(m), bits, s).bit_reverse_rows(), lambda mats: mmcs.commit(mats)[0])
         assert np.asarray(cap).tolist() == gold["main_cap"]
     default_poseidon2(BabyBear, 16).upload(gpu)                        # restore the default constants for the other tests
-
-
-@pytest.mark.parametrize("f,log_h,w,added_bits", [(KoalaBear, 12, 100, 1), (BabyBear, 13, 36, 2), (KoalaBear, 16, 20, 1), (KoalaBear, 14, 12, 1),
-                                                  (BabyBear, 17, 44, 1), (KoalaBear, 20, 28, 1), (BabyBear, 15, 300, 1), (KoalaBear, 18, 132, 1)])
-def test_lde_last_pass_half_sector_variant(gpu, f, log_h, w, added_bits, monkeypatch):
-    """Row pitch = 16 mod 32 bytes (w % 8 == 4): the last LDE pass runs the HS variant of the pipelined kernel (column-tile runs per
-    group, odd-row results parked in shared memory and stored as whole sectors with the next tile).  It must equal the plain
-    variant bit for bit, and the oracle where that is fast enough; also through the chunked host-trace commit."""
-    g = torch.Generator(device="cuda"); g.manual_seed(log_h * 1000 + w)
-    x = torch.randint(0, f.P, (1 << log_h, w), device="cuda", dtype=torch.int32, generator=g)
-    dft = Radix2DitParallel(f, gpu)
-    monkeypatch.setenv("P3GPU_NTT_HALFSECTOR", "1")
-    got = dft.coset_lde_batch(x, added_bits, f.generator).bit_reverse_rows()
-    monkeypatch.setenv("P3GPU_NTT_HALFSECTOR", "0")
-    ref = dft.coset_lde_batch(x, added_bits, f.generator).bit_reverse_rows()
-    assert torch.equal(got, ref)
-    if log_h <= 14:
-        assert np.array_equal(host(got), O.coset_lde_batch(f.id, host(x), added_bits, f.generator, bitrev_out=True))
-    if log_h <= 17:
-        monkeypatch.setenv("P3GPU_NTT_HALFSECTOR", "1")
-        monkeypatch.setenv("P3GPU_E2E_CHUNKS", "3")
-        default_poseidon2(f, 16).upload(gpu)
-        cap, lde, layers = gpu.pcs_commit_host(f.id, _lib.HASH_POSEIDON2_W16, host(x), added_bits, 0)
-        assert torch.equal(lde, ref)
