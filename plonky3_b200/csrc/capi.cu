@@ -109,6 +109,12 @@ void p3gpu_ctx_destroy(p3gpu_ctx *ctx) {
     if (ctx->scratch) cudaFree(ctx->scratch);
     if (ctx->scratch2) cudaFree(ctx->scratch2);
     for (int i = 0; i < 4; i++) if (ctx->pool[i]) cudaFree(ctx->pool[i]);
+    if (ctx->xchg_stream) cudaStreamDestroy(ctx->xchg_stream);
+    for (int q = 0; q < 16; q++) if (ctx->dma_stream[q]) { cudaStreamDestroy(ctx->dma_stream[q]); cudaEventDestroy(ctx->dma_done[q]); }
+    for (int b = 0; b < 2; b++) {
+        if (ctx->ev_stage_full[b]) { cudaEventDestroy(ctx->ev_stage_full[b]); cudaEventDestroy(ctx->ev_stage_free[b]); }
+        if (ctx->stage_buf[b]) cudaFree(ctx->stage_buf[b]);
+    }
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
@@ -597,7 +603,7 @@ int32_t p3gpu_coset_lde_batch_sharded_dev(p3gpu_ctx *ctx, int field, const p3gpu
                                           unsigned added_bits, uint32_t shift, size_t w_total, size_t col_off) {
     P3_ENTER(ctx);
     P3_TRY(check_group(grp, true));
-    P3_CHECK(d_in != nullptr, P3GPU_EINVAL, "null argument");
+    P3_CHECK(d_in != nullptr || w_local == 0, P3GPU_EINVAL, "null argument");
     return ntt_coset_lde_sharded(ctx, field, d_in, h, w_local, added_bits, shift, grp->world, grp->rows, w_total, col_off);
 }
 
@@ -607,7 +613,7 @@ int32_t p3gpu_commit_sharded_dev(p3gpu_ctx *ctx, int field, int hash, const p3gp
                                  uint32_t *d_sub_layers, size_t *layer_lens, size_t *n_layers, uint32_t *h_cap, size_t *cap_len, float *phase_ms) {
     P3_ENTER(ctx);
     P3_TRY(check_group(grp, true));
-    P3_CHECK(epoch && d_evals_local && d_sub_layers && layer_lens && n_layers && h_cap && cap_len, P3GPU_EINVAL, "null argument");
+    P3_CHECK(epoch && (d_evals_local || w_local == 0) && d_sub_layers && layer_lens && n_layers && h_cap && cap_len, P3GPU_EINVAL, "null argument");
     P3_CHECK(field == BABY_BEAR || field == KOALA_BEAR, P3GPU_EUNSUPPORTED, "unknown field %d", field);
     const unsigned world = grp->world, rank = grp->rank, log_g = log2_floor(world);
     const size_t H = h << log_blowup, rows = H / world;

@@ -88,6 +88,7 @@ struct p3gpu_ctx {
     void *chunk_out[2] = {nullptr, nullptr}; size_t chunk_out_bytes[2] = {0, 0};
     // staged multi-GPU exchange: staging buffers (one LDE'd column chunk each), exchange stream and events
     cudaStream_t xchg_stream = nullptr;
+    cudaStream_t dma_stream[16] = {nullptr}; cudaEvent_t dma_done[16] = {nullptr};   // dma exchange: one copy stream per destination rank
     cudaEvent_t ev_stage_full[2] = {nullptr, nullptr}, ev_stage_free[2] = {nullptr, nullptr};
     void *stage_buf[2] = {nullptr, nullptr}; size_t stage_bytes[2] = {0, 0};   // device copy of the per-height matrix table (> 8 matrices)
     // FRI half-inverse-power tables (bit-reversed), one per field, grown on demand

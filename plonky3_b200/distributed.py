@@ -227,7 +227,7 @@ class PeerGroup:
         """p3gpu_commit_sharded_dev.  Returns (cap (n, 8) uint32 array — identical on every rank, my sub-tree's digest
         layers as CUDA tensors, [lde_ms, barrier_ms, hash_ms, cap_exchange_ms] or None)."""
         gpu = self.gpu
-        m = gpu._dev(evals_local)
+        m = gpu._dev(evals_local)                                    # (h, w_local); w_local may be 0 (more ranks than column units)
         h, w_local = int(m.shape[0]), int(m.shape[1])
         assert (h << log_blowup) == self.rows_per_rank * self.world
         gpu._use_torch_stream()

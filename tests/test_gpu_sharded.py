@@ -91,7 +91,7 @@ def _rank_main(rank, world, port, q):
             olayers = O.merkle_tree(ohs, [elde])
             exp_cap = O.merkle_cap(olayers, cap_height)
             c0, c1 = column_block(w, world, rank, align=8)
-            local = torch.from_numpy(np.ascontiguousarray(full[:, c0:c1]).view(np.int32)).cuda()
+            local = torch.from_numpy(np.ascontiguousarray(full[:, c0:c1]).view(np.int32)).cuda()   # may be EMPTY: more ranks than column units
             for _ in range(2):                               # twice: the epoch counter and the row blocks are reused
                 cap, layers, ph = grp.commit(f, hash_kind, local, c0, 1, cap_height, phases=True)
             rows = H // world
@@ -125,5 +125,4 @@ def test_sharded_commit_equals_single_commit(world):
     for p in procs: p.start()
     res = [q.get(timeout=600) for _ in range(world)]
     for p in procs: p.join(timeout=60)
-    for rank, ok, msg in sorted(res):
-        assert ok, f"rank {rank}: {msg}"
+    assert all(ok for _, ok, _ in res), "; ".join(f"rank {r}: {m}" for r, ok, m in sorted(res) if not ok)
