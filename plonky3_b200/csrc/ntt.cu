@@ -1298,7 +1298,7 @@ int32_t ntt_coset_lde_sharded(p3gpu_ctx *ctx, int field, const u32 *d_in, size_t
     //   dma    : (default) as staged, with one 2-D peer copy per destination on the copy engines instead of the push kernel
     //            (2.23 ms / 41.6 ms with 64-column chunks; LDE alone 1.42 ms / NCCL all_to_all baseline 45.3 ms).
     const char *mode = getenv("P3GPU_SHARD_MODE");
-    if (!mode) mode = "dma";
+    if (!mode) mode = world == 1 ? "fused" : "dma";   // a single rank owns every row: store straight into its block, nothing to exchange
     if (mode && strcmp(mode, "fused") == 0) {
         bool done = false;
         if (field == BABY_BEAR) P3_TRY(lde_tiled_impl<BABY_BEAR>(ctx, d_in, h, w_local, added_bits, shift, nullptr, &done, &sh));
