@@ -80,24 +80,6 @@ template <int F, int K> __device__ __forceinline__ u32 div_2exp(u32 x) {
     const u32 c = (x + mask) >> K;
     return c + m * C;
 }
-// x * 2^-k as a Shoup multiplication by the compile-time constant w = 2^-k mod p (canonical; multiplying the Montgomery form of x
-// by a canonical constant keeps the Montgomery scaling): IMAD.HI + 2 IMAD + one VIADDMNMX = 3 multiply-pipe + 1 ALU instruction
-// against 1 + 4-5 for div_2exp.  The sponge kernels are bound by the ALU pipe (ncu: ALU 70 %, multiply-capable FMA pipe 35 %), so
-// moving the 17 (width 24) / 8 (width 16) shift entries of every internal round to the half-idle pipe shortens the critical pipe.
-#ifndef P3_DIAG_SHOUP
-#define P3_DIAG_SHOUP 1
-#endif
-template <int F> __host__ __device__ constexpr u32 inv_2exp_canonical(int k) {
-    u64 v = 1;
-    for (int i = 0; i < k; i++) v = v * ((Fp<F>::P + 1ull) / 2) % Fp<F>::P;
-    return (u32)v;
-}
-template <int F, int K> __device__ __forceinline__ u32 div_2exp_shoup(u32 x) {
-    constexpr u32 Wc = inv_2exp_canonical<F>(K);
-    constexpr u32 Wq = (u32)((((u64)Wc) << 32) / Fp<F>::P);
-    uint2 tw; tw.x = Wc; tw.y = Wq;
-    return fp_reduce<F>(shoup_mul<F>(x, tw));
-}
 template <int F, int W, int I> __device__ __forceinline__ u32 diag_mul_add(u32 x, u32 sum) {
     constexpr DiagEntry d = Diag<F, W>::at(I);
     constexpr int am = d.mul < 0 ? -d.mul : d.mul;
@@ -108,12 +90,7 @@ template <int F, int W, int I> __device__ __forceinline__ u32 diag_mul_add(u32 x
         if (am == 3) v = fp_add<F>(fp_double<F>(x), x);
         if (am == 4) v = fp_double<F>(fp_double<F>(x));
     } else {
-#if P3_DIAG_SHOUP
-        if constexpr (-d.shift >= 2) v = div_2exp_shoup<F, -d.shift>(x);
-        else v = div_2exp<F, 1>(x);     // halves: 4 cheap ALU instructions
-#else
         v = div_2exp<F, -d.shift>(x);   // also covers the halves (k = 1)
-#endif
     }
     return d.mul < 0 ? fp_sub<F>(sum, v) : fp_add<F>(sum, v);
 }
