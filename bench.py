@@ -424,7 +424,7 @@ def main():
 def sharded_commit(gpu, world, rank, dev, barrier, max_over_ranks, KB, _lib, torch, dist, np):
     """One config-5 trace (2^20 x 1312, every rank derives the same synthetic trace from the same seed and keeps its column
     block), committed across the ranks.  Returns per-mode ms (max over ranks, CUDA events), phases and the cap check."""
-    from plonky3_b200.distributed import GpuBackend, PeerGroup, column_block, commit_bit_exact, commit_column_blocks
+    from plonky3_b200.distributed import GpuBackend, PeerGroup, column_block, column_starts, commit_bit_exact, commit_column_blocks
     h, H = 1 << T_LOG_H, 2 << T_LOG_H
     gt = torch.Generator(device=dev); gt.manual_seed(12345)
     full = torch.randint(0, KB.P, (h, T_W), device=dev, dtype=torch.int32, generator=gt)
@@ -460,12 +460,12 @@ def sharded_commit(gpu, world, rank, dev, barrier, max_over_ranks, KB, _lib, tor
     # mode `peer`: the product path
     grp = PeerGroup(gpu, H // world, T_W)
     phases = np.zeros(4)
-    cap, _, _ = grp.commit(KB, _lib.HASH_POSEIDON2_W24, local, c0, 1, T_CAP)
+    cap, _, _ = grp.commit(KB, _lib.HASH_POSEIDON2_W24, local, column_starts(T_W, world, align=8), 1, T_CAP)
     ok_peer = bool(np.array_equal(cap, cap_ref))
 
     def peer_step():
         nonlocal phases
-        _, _, ph = grp.commit(KB, _lib.HASH_POSEIDON2_W24, local, c0, 1, T_CAP, phases=True)
+        _, _, ph = grp.commit(KB, _lib.HASH_POSEIDON2_W24, local, column_starts(T_W, world, align=8), 1, T_CAP, phases=True)
         phases = phases + np.array(ph)
     phases[:] = 0
     t_peer = ev_time(peer_step)

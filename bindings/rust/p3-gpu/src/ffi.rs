@@ -87,9 +87,10 @@ unsafe extern "C" {
     pub fn p3gpu_ipc_close(ctx: *mut P3GpuCtx, dptr: *mut c_void) -> i32;
     pub fn p3gpu_peer_barrier_dev(ctx: *mut P3GpuCtx, grp: *const P3GpuPeerGroup, epoch: u32) -> i32;
     pub fn p3gpu_commit_sharded_dev(ctx: *mut P3GpuCtx, field: c_int, hash: c_int, grp: *const P3GpuPeerGroup, epoch: *mut u32,
-                                    d_evals_local: *const u32, h: usize, w_local: usize, w_total: usize, col_off: usize, log_blowup: c_uint,
+                                    d_evals_local: *const u32, h: usize, col_starts: *const usize, log_blowup: c_uint,
                                     cap_height: c_uint, d_sub_layers: *mut u32, layer_lens: *mut usize, n_layers: *mut usize, h_cap: *mut u32,
                                     cap_len: *mut usize, phase_ms: *mut f32) -> i32;
+    pub fn p3gpu_shard_chunk_bounds(w_local: usize, bounds: *mut usize, max_bounds: usize) -> usize;
 }
 
 /// The reference's prover-side trait methods have no `Result`: shape violations panic (`log2_strict_usize`,

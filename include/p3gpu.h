@@ -279,16 +279,24 @@ int32_t p3gpu_coset_lde_batch_sharded_dev(p3gpu_ctx *ctx, int field, const p3gpu
                                           size_t w_local, unsigned added_bits, uint32_t shift, size_t w_total, size_t col_off);
 
 /* TwoAdicFriPcs::commit (two_adic_pcs.rs:300-324) of ONE trace sharded by column block over the group; bit-identical to
- * the single-GPU commitment: sharded LDE (above) -> barrier -> leaf hashing + sub-tree over grp->rows[rank] -> exchange
+ * the single-GPU commitment: sharded LDE -> barrier -> leaf hashing + sub-tree over grp->rows[rank] -> exchange
  * of the cap slices -> barrier -> (cap_height < log2(world): top levels compressed redundantly on every rank).
+ * col_starts: world + 1 column offsets, rank g holds columns [col_starts[g], col_starts[g+1]) of the trace (every rank passes the
+ *   same array; blocks that are multiples of 8 columns keep all copies sector aligned; a block may be empty); d_evals_local: my
+ *   block, h x (col_starts[rank+1] - col_starts[rank]).
  * *epoch: the group's barrier epoch counter (start at 0; same variable for every collective call of this group).
+ * Row-block layout after the call (world > 1): CHUNK-MAJOR — for every source rank g and every column chunk [b, b') of its block
+ *   (p3gpu_shard_chunk_bounds of the block width) one contiguous (H/world) x (b' - b) row-major matrix at element offset
+ *   (H/world) * (col_starts[g] + b); with world == 1 the block is the dense (H x w_total) LDE.
  * d_sub_layers: p3gpu_merkle_total_digests(H / world) digests = this rank's sub-tree (kept for openings);
  * h_cap: 2^cap_height digests (host), identical on every rank.  phase_ms (NULL or 4 floats): device time of
- * [LDE + peer stores, barrier wait, hashing, cap exchange]. */
+ * [LDE + exchange, barrier wait, hashing, cap exchange]. */
 int32_t p3gpu_commit_sharded_dev(p3gpu_ctx *ctx, int field, int hash, const p3gpu_peer_group *grp, uint32_t *epoch,
-                                 const uint32_t *d_evals_local, size_t h, size_t w_local, size_t w_total, size_t col_off,
+                                 const uint32_t *d_evals_local, size_t h, const size_t *col_starts,
                                  unsigned log_blowup, unsigned cap_height, uint32_t *d_sub_layers, size_t *layer_lens,
                                  size_t *n_layers, uint32_t *h_cap, size_t *cap_len, float *phase_ms);
+/* the column chunk boundaries (0 = first, w_local = last) a block of w_local columns is exchanged in; returns their number */
+size_t p3gpu_shard_chunk_bounds(size_t w_local, size_t *bounds, size_t max_bounds);
 
 #ifdef __cplusplus
 }

@@ -27,7 +27,7 @@ EXPORTS = [
     "p3gpu_challenger_new", "p3gpu_challenger_free", "p3gpu_challenger_clone", "p3gpu_challenger_observe_dev", "p3gpu_challenger_observe",
     "p3gpu_challenger_sample", "p3gpu_challenger_grind", "p3gpu_gather_rows_dev", "p3gpu_merkle_paths_dev",
     "p3gpu_ipc_export", "p3gpu_ipc_import", "p3gpu_ipc_close", "p3gpu_memset_dev", "p3gpu_peer_barrier_dev",
-    "p3gpu_peer_allgather_dev", "p3gpu_coset_lde_batch_sharded_dev", "p3gpu_commit_sharded_dev",
+    "p3gpu_peer_allgather_dev", "p3gpu_coset_lde_batch_sharded_dev", "p3gpu_commit_sharded_dev", "p3gpu_shard_chunk_bounds",
 ]
 
 PEER_CTRL_BYTES, PEER_CTRL_USER = 65536, 256
@@ -110,7 +110,8 @@ def load():
         "p3gpu_peer_barrier_dev": (i32, [vp, vp, u32]),
         "p3gpu_peer_allgather_dev": (i32, [vp, vp, sz, vp, sz]),
         "p3gpu_coset_lde_batch_sharded_dev": (i32, [vp, ci, vp, vp, sz, sz, cu, u32, sz, sz]),
-        "p3gpu_commit_sharded_dev": (i32, [vp, ci, ci, vp, vp, vp, sz, sz, sz, sz, cu, cu, vp, vp, vp, vp, vp, vp]),
+        "p3gpu_commit_sharded_dev": (i32, [vp, ci, ci, vp, vp, vp, sz, vp, cu, cu, vp, vp, vp, vp, vp, vp]),
+        "p3gpu_shard_chunk_bounds": (sz, [sz, vp, sz]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)

@@ -607,15 +607,25 @@ int32_t p3gpu_coset_lde_batch_sharded_dev(p3gpu_ctx *ctx, int field, const p3gpu
     return ntt_coset_lde_sharded(ctx, field, d_in, h, w_local, added_bits, shift, grp->world, grp->rows, w_total, col_off);
 }
 
+size_t p3gpu_shard_chunk_bounds(size_t w_local, size_t *bounds, size_t max_bounds) {
+    const std::vector<size_t> cb = shard_chunk_bounds(w_local);
+    for (size_t i = 0; i < cb.size() && i < max_bounds; i++) bounds[i] = cb[i];
+    return cb.size();
+}
+
 // TwoAdicFriPcs::commit of ONE trace whose columns are sharded over the ranks, bit-identical to the single-GPU commitment.
 int32_t p3gpu_commit_sharded_dev(p3gpu_ctx *ctx, int field, int hash, const p3gpu_peer_group *grp, uint32_t *epoch, const uint32_t *d_evals_local,
-                                 size_t h, size_t w_local, size_t w_total, size_t col_off, unsigned log_blowup, unsigned cap_height,
+                                 size_t h, const size_t *col_starts, unsigned log_blowup, unsigned cap_height,
                                  uint32_t *d_sub_layers, size_t *layer_lens, size_t *n_layers, uint32_t *h_cap, size_t *cap_len, float *phase_ms) {
     P3_ENTER(ctx);
     P3_TRY(check_group(grp, true));
-    P3_CHECK(epoch && (d_evals_local || w_local == 0) && d_sub_layers && layer_lens && n_layers && h_cap && cap_len, P3GPU_EINVAL, "null argument");
+    P3_CHECK(epoch && col_starts && d_sub_layers && layer_lens && n_layers && h_cap && cap_len, P3GPU_EINVAL, "null argument");
     P3_CHECK(field == BABY_BEAR || field == KOALA_BEAR, P3GPU_EUNSUPPORTED, "unknown field %d", field);
     const unsigned world = grp->world, rank = grp->rank, log_g = log2_floor(world);
+    for (unsigned g = 0; g < world; g++) P3_CHECK(col_starts[g] <= col_starts[g + 1], P3GPU_EINVAL, "column blocks must be ordered");
+    P3_CHECK(col_starts[0] == 0, P3GPU_EINVAL, "column blocks must start at 0");
+    const size_t w_total = col_starts[world], col_off = col_starts[rank], w_local = col_starts[rank + 1] - col_off;
+    P3_CHECK(d_evals_local || w_local == 0, P3GPU_EINVAL, "null argument");
     const size_t H = h << log_blowup, rows = H / world;
     const double tmo = grp->timeout_s > 0 ? grp->timeout_s : 20.0;
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -625,16 +635,31 @@ int32_t p3gpu_commit_sharded_dev(p3gpu_ctx *ctx, int field, int hash, const p3gp
     // every rank has entered this call
     P3_TRY(peer_barrier(ctx, world, rank, grp->ctrl, ++*epoch, tmo));
     P3_TRY(mark(0));
-    // 1) LDE of my column block; its last pass stores every tile into the row block of the rank that will hash those rows
+    // 1) LDE of my column block, exchanged chunk by chunk into the row blocks of the ranks that will hash those rows.  With more
+    //    than one rank the row blocks are CHUNK-MAJOR: every (source rank, column chunk) is its own contiguous (rows x chunk width)
+    //    matrix at element offset rows * (first column of the chunk), so the exchange is a plain contiguous copy at link rate and
+    //    the leaf sponge runs over the chunk matrices in column order — the same digest as over the dense row (merkle_tree.rs:312-316)
+    const int chunk_major = world > 1;
     const u32 shift = field == BABY_BEAR ? to_monty<BABY_BEAR>(Fp<BABY_BEAR>::GEN) : to_monty<KOALA_BEAR>(Fp<KOALA_BEAR>::GEN);
-    P3_TRY(ntt_coset_lde_sharded(ctx, field, d_evals_local, h, w_local, log_blowup, shift, world, grp->rows, w_total, col_off));
+    P3_TRY(ntt_coset_lde_sharded(ctx, field, d_evals_local, h, w_local, log_blowup, shift, world, grp->rows, w_total, col_off, chunk_major));
     P3_TRY(mark(1));
-    // 2) all ranks' stores into my row block have landed
+    // 2) all ranks' chunks have landed in my row block
     P3_TRY(peer_barrier(ctx, world, rank, grp->ctrl, ++*epoch, tmo));
     P3_TRY(mark(2));
     // 3) my rows are a complete sub-tree of the global tree (rows of the bit-reversed LDE, merkle_tree.rs:268-338)
-    const u32 *mats[1] = {grp->rows[rank]};
-    P3_TRY(hash_merkle_commit(ctx, field, hash, 1, mats, &rows, &w_total, d_sub_layers, layer_lens, n_layers));
+    std::vector<const u32 *> mats;
+    std::vector<size_t> hs, ws;
+    if (!chunk_major) { mats.push_back(grp->rows[rank]); hs.push_back(rows); ws.push_back(w_total); }
+    else
+        for (unsigned g = 0; g < world; g++) {
+            const std::vector<size_t> cb = shard_chunk_bounds(col_starts[g + 1] - col_starts[g]);
+            for (size_t c = 0; c + 1 < cb.size(); c++) {
+                if (cb[c + 1] == cb[c]) continue;
+                mats.push_back(grp->rows[rank] + rows * (col_starts[g] + cb[c]));
+                hs.push_back(rows); ws.push_back(cb[c + 1] - cb[c]);
+            }
+        }
+    P3_TRY(hash_merkle_commit(ctx, field, hash, mats.size(), mats.data(), hs.data(), ws.data(), d_sub_layers, layer_lens, n_layers));
     P3_TRY(mark(3));
     // 4) exchange the slice of every sub-tree that the cap (or the levels above the sub-tree roots) is made of
     const size_t nl = *n_layers;

@@ -1270,8 +1270,22 @@ int32_t ntt_coset_lde(p3gpu_ctx *ctx, int field, const u32 *d_in, size_t h, size
 }
 
 // Column-sharded coset LDE whose result lands row-sharded on all ranks (column blocks -> all-to-all -> row blocks).
+// Column chunks a rank's block of w_local columns is exchanged in (boundaries multiples of 8 columns; P3GPU_SHARD_CHUNK, default
+// 64).  Every rank computes the same list for every source rank: the chunk-major row-block layout depends on it.
+std::vector<size_t> shard_chunk_bounds(size_t w_local) {
+    const size_t chunk = (size_t)std::max(8, env_int("P3GPU_SHARD_CHUNK", 64) & ~7);
+    const size_t n_chunks = std::max<size_t>(1, (w_local + chunk / 2) / chunk);
+    std::vector<size_t> cb{0};
+    for (size_t c = 1; c <= n_chunks; c++) {
+        const size_t b = c == n_chunks ? w_local : (w_local * c / n_chunks) & ~(size_t)7;
+        if (b > cb.back()) cb.push_back(b);
+    }
+    if (cb.back() != w_local) cb.push_back(w_local);
+    return cb;
+}
+
 int32_t ntt_coset_lde_sharded(p3gpu_ctx *ctx, int field, const u32 *d_in, size_t h, size_t w_local, unsigned added_bits, u32 shift,
-                              unsigned world, u32 *const *rank_out, size_t w_total, size_t col_off) {
+                              unsigned world, u32 *const *rank_out, size_t w_total, size_t col_off, int chunk_major) {
     P3_CHECK(added_bits <= 8, P3GPU_EINVAL, "added_bits %u too large", added_bits);
     if (w_local == 0) {   // a rank without columns (more ranks than column units) only takes part in the barriers and the hashing
         P3_TRY(check_shape(field, h, 1, added_bits));
@@ -1299,7 +1313,8 @@ int32_t ntt_coset_lde_sharded(p3gpu_ctx *ctx, int field, const u32 *d_in, size_t
     //            (2.23 ms / 41.6 ms with 64-column chunks; LDE alone 1.42 ms / NCCL all_to_all baseline 45.3 ms).
     const char *mode = getenv("P3GPU_SHARD_MODE");
     if (!mode) mode = world == 1 ? "fused" : "dma";   // a single rank owns every row: store straight into its block, nothing to exchange
-    if (mode && strcmp(mode, "fused") == 0) {
+    if (chunk_major && world > 1 && strcmp(mode, "fused") == 0) mode = "dma";   // the fused stores know the row-major layout only
+    if (mode && strcmp(mode, "fused") == 0 && !(chunk_major && world > 1)) {
         bool done = false;
         if (field == BABY_BEAR) P3_TRY(lde_tiled_impl<BABY_BEAR>(ctx, d_in, h, w_local, added_bits, shift, nullptr, &done, &sh));
         else P3_TRY(lde_tiled_impl<KOALA_BEAR>(ctx, d_in, h, w_local, added_bits, shift, nullptr, &done, &sh));
@@ -1315,10 +1330,7 @@ int32_t ntt_coset_lde_sharded(p3gpu_ctx *ctx, int field, const u32 *d_in, size_t
         }
     }
     const unsigned sh_rank_hint = (unsigned)((col_off * world) / std::max<size_t>(w_total, 1));   // ~ my rank: staggers the peers' copy order
-    size_t chunk = (size_t)std::max(8, env_int("P3GPU_SHARD_CHUNK", 64) & ~7);
-    const size_t n_chunks = std::max<size_t>(1, (w_local + chunk / 2) / chunk);
-    std::vector<size_t> cb{0};
-    for (size_t c = 1; c <= n_chunks; c++) cb.push_back(c == n_chunks ? w_local : (w_local * c / n_chunks) & ~(size_t)7);
+    const std::vector<size_t> cb = shard_chunk_bounds(w_local);
     size_t wmax = 0;
     for (size_t c = 0; c + 1 < cb.size(); c++) wmax = std::max(wmax, cb[c + 1] - cb[c]);
     for (int b = 0; b < 2; b++) {
@@ -1351,13 +1363,17 @@ int32_t ntt_coset_lde_sharded(p3gpu_ctx *ctx, int field, const u32 *d_in, size_t
                     P3_CUDA(cudaEventCreateWithFlags(&ctx->dma_done[dq], cudaEventDisableTiming));
                 }
                 P3_CUDA(cudaStreamWaitEvent(ctx->dma_stream[dq], ctx->ev_stage_full[b], 0));
-                P3_CUDA(cudaMemcpy2DAsync(rank_out[dq] + col_off + c0, w_total * 4, S + (size_t)dq * R * wc, wc * 4, wc * 4, R, cudaMemcpyDeviceToDevice,
-                                          ctx->dma_stream[dq]));
+                if (chunk_major)   // the chunk is one contiguous (R x wc) matrix on both sides: a plain copy at link rate
+                    P3_CUDA(cudaMemcpyAsync(rank_out[dq] + R * (col_off + c0), S + (size_t)dq * R * wc, R * wc * 4, cudaMemcpyDeviceToDevice, ctx->dma_stream[dq]));
+                else
+                    P3_CUDA(cudaMemcpy2DAsync(rank_out[dq] + col_off + c0, w_total * 4, S + (size_t)dq * R * wc, wc * 4, wc * 4, R, cudaMemcpyDeviceToDevice,
+                                              ctx->dma_stream[dq]));
                 P3_CUDA(cudaEventRecord(ctx->dma_done[dq], ctx->dma_stream[dq]));
                 P3_CUDA(cudaStreamWaitEvent(ctx->xchg_stream, ctx->dma_done[dq], 0));
             }
         } else {
-            P3_TRY(peer_push_rows(ctx, ctx->xchg_stream, world, rank_out, S, H, wc, w_total, col_off + c0, sh.log_rows));
+            if (chunk_major) P3_TRY(peer_push_rows(ctx, ctx->xchg_stream, world, rank_out, S, H, wc, wc, ((size_t)1 << sh.log_rows) * (col_off + c0), sh.log_rows));
+            else P3_TRY(peer_push_rows(ctx, ctx->xchg_stream, world, rank_out, S, H, wc, w_total, col_off + c0, sh.log_rows));
         }
         P3_CUDA(cudaEventRecord(ctx->ev_stage_free[b], ctx->xchg_stream));
     }

@@ -24,6 +24,11 @@ import torch
 import torch.distributed as dist
 
 
+def column_starts(width: int, world: int, align: int = 1):
+    """The world + 1 offsets of the `column_block` split."""
+    return [column_block(width, world, r, align)[0] for r in range(world)] + [width]
+
+
 def column_block(width: int, world: int, rank: int, align: int = 1):
     """Contiguous column block of `rank` in units of `align` columns: the first (width/align) % world ranks get one extra
     unit, the last rank also takes the width % align remainder.  align = 8 keeps every 32-byte segment the LDE's last pass
@@ -223,26 +228,56 @@ class PeerGroup:
         check(self.gpu.L.p3gpu_coset_lde_batch_sharded_dev(self.gpu.h, field.id, C.byref(self.struct), m.data_ptr(), m.shape[0], m.shape[1],
                                                           added_bits, shift, self.w_total, col_off))
 
-    def commit(self, field, hash_kind: int, evals_local, col_off: int, log_blowup: int, cap_height: int, phases: bool = False):
-        """p3gpu_commit_sharded_dev.  Returns (cap (n, 8) uint32 array — identical on every rank, my sub-tree's digest
-        layers as CUDA tensors, [lde_ms, barrier_ms, hash_ms, cap_exchange_ms] or None)."""
+    def commit(self, field, hash_kind: int, evals_local, col_starts, log_blowup: int, cap_height: int, phases: bool = False):
+        """p3gpu_commit_sharded_dev.  `col_starts`: world + 1 column offsets (rank g holds [col_starts[g], col_starts[g+1]));
+        an int is taken as my own offset of an even `column_block` split, for callers that do not know the others' blocks.
+        Returns (cap (n, 8) uint32 array — identical on every rank, my sub-tree's digest layers as CUDA tensors,
+        [lde_ms, barrier_ms, hash_ms, cap_exchange_ms] or None).  With world > 1 my row block is left chunk-major
+        (`row_block_dense` reassembles it)."""
         gpu = self.gpu
         m = gpu._dev(evals_local)                                    # (h, w_local); w_local may be 0 (more ranks than column units)
         h, w_local = int(m.shape[0]), int(m.shape[1])
         assert (h << log_blowup) == self.rows_per_rank * self.world
+        if isinstance(col_starts, int):
+            raise TypeError("PeerGroup.commit needs the world + 1 column offsets of all ranks (column_starts(...))")
+        starts = [int(x) for x in col_starts]
+        assert len(starts) == self.world + 1 and starts[-1] == self.w_total and starts[self.rank + 1] - starts[self.rank] == w_local
+        self.col_starts = starts
+        cs = (C.c_size_t * (self.world + 1))(*starts)
         gpu._use_torch_stream()
         tot = gpu.merkle_total_digests(self.rows_per_rank)
         layers = gpu._empty((tot, 8))
         lens = (C.c_size_t * 65)(); nl = C.c_size_t()
         cap = np.zeros((max(1 << cap_height, self.world), 8), dtype=np.uint32); cap_len = C.c_size_t()
         ph = (C.c_float * 4)() if phases else None
-        check(gpu.L.p3gpu_commit_sharded_dev(gpu.h, field.id, hash_kind, C.byref(self.struct), C.byref(self.epoch), m.data_ptr(), h, w_local,
-                                             self.w_total, col_off, log_blowup, cap_height, layers.data_ptr(), lens, C.byref(nl),
+        check(gpu.L.p3gpu_commit_sharded_dev(gpu.h, field.id, hash_kind, C.byref(self.struct), C.byref(self.epoch), m.data_ptr(), h, cs,
+                                             log_blowup, cap_height, layers.data_ptr(), lens, C.byref(nl),
                                              cap.ctypes.data, C.byref(cap_len), ph))
         out, off = [], 0
         for k in range(nl.value):
             out.append(layers[off:off + lens[k]]); off += lens[k]
         return cap[: cap_len.value].copy(), out, ([float(x) for x in ph] if phases else None)
+
+    def chunk_bounds(self, w_local: int):
+        b = (C.c_size_t * (w_local // 8 + 3))()
+        n = self.gpu.L.p3gpu_shard_chunk_bounds(w_local, b, len(b))
+        return [int(b[i]) for i in range(n)]
+
+    def row_block_dense(self, col_starts=None):
+        """My row block as a dense (rows_per_rank, w_total) tensor (a copy), whatever layout the last commit left it in."""
+        starts = col_starts if col_starts is not None else self.col_starts
+        R = self.rows_per_rank
+        if self.world == 1:
+            return self.rows_tensor().clone()
+        flat = self.rows_tensor().reshape(-1)
+        out = torch.empty((R, self.w_total), dtype=flat.dtype, device=flat.device)
+        for g in range(self.world):
+            cb = self.chunk_bounds(starts[g + 1] - starts[g])
+            for a, b in zip(cb[:-1], cb[1:]):
+                if b > a:
+                    c0 = starts[g] + a
+                    out[:, c0:c0 + (b - a)] = flat[R * c0: R * (c0 + b - a)].reshape(R, b - a)
+        return out
 
     def close(self):
         for p in self._imported:

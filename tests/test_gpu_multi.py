@@ -22,7 +22,7 @@ def _worker(rank, world, port, q):
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(f"cuda:{rank}"))
         from oracle import p3_oracle as O
         from plonky3_b200 import _lib
-        from plonky3_b200.distributed import GpuBackend, column_block, commit_bit_exact, commit_column_blocks
+        from plonky3_b200.distributed import GpuBackend, column_block, column_starts, commit_bit_exact, commit_column_blocks
         from plonky3_b200.field import KoalaBear as f
         from plonky3_b200.gpu import Gpu
         from plonky3_b200.poseidon2 import default_poseidon2
@@ -49,10 +49,10 @@ def _worker(rank, world, port, q):
         a0, a1 = column_block(W, world, rank, align=8)
         loc8 = torch.from_numpy(np.ascontiguousarray(full[:, a0:a1]).view(np.int32)).cuda()
         for _ in range(3):
-            pcap, players, ph = grp.commit(f, _lib.HASH_POSEIDON2_W24, loc8, a0, 1, CAP_H, phases=True)
+            pcap, players, ph = grp.commit(f, _lib.HASH_POSEIDON2_W24, loc8, column_starts(W, world, align=8), 1, CAP_H, phases=True)
         ok = ok and np.array_equal(pcap, exp_cap)
         rows = H // world
-        ok = ok and np.array_equal(grp.rows_tensor().cpu().numpy().view(np.uint32), lde_full[rank * rows:(rank + 1) * rows])
+        ok = ok and np.array_equal(grp.row_block_dense().cpu().numpy().view(np.uint32), lde_full[rank * rows:(rank + 1) * rows])
         dist.barrier()
         grp.close()
         q.put((rank, bool(ok), bool(ok2), ""))

@@ -13,7 +13,7 @@ import torch
 from oracle import p3_oracle as O
 
 from plonky3_b200 import _lib
-from plonky3_b200.distributed import PeerGroup, column_block
+from plonky3_b200.distributed import PeerGroup, column_block, column_starts
 from plonky3_b200.field import BabyBear, KoalaBear
 from plonky3_b200.gpu import Gpu
 from plonky3_b200.poseidon2 import default_poseidon2
@@ -93,10 +93,10 @@ def _rank_main(rank, world, port, q):
             c0, c1 = column_block(w, world, rank, align=8)
             local = torch.from_numpy(np.ascontiguousarray(full[:, c0:c1]).view(np.int32)).cuda()   # may be EMPTY: more ranks than column units
             for _ in range(2):                               # twice: the epoch counter and the row blocks are reused
-                cap, layers, ph = grp.commit(f, hash_kind, local, c0, 1, cap_height, phases=True)
+                cap, layers, ph = grp.commit(f, hash_kind, local, column_starts(w, world, align=8), 1, cap_height, phases=True)
             rows = H // world
             good = np.array_equal(cap, exp_cap) and len(ph) == 4
-            good = good and np.array_equal(host(grp.rows_tensor()), elde[rank * rows:(rank + 1) * rows])
+            good = good and np.array_equal(host(grp.row_block_dense()), elde[rank * rows:(rank + 1) * rows])
             for k, lay in enumerate(layers):                 # my sub-tree = slice `rank` of the global tree's lower layers
                 n = max(rows >> k, 1)
                 good = good and np.array_equal(host(lay)[:n], olayers[k][rank * n:(rank + 1) * n])
