@@ -93,3 +93,31 @@ def test_column_block_partition():
             assert blocks[0][0] == 0 and blocks[-1][1] == w
             assert all(blocks[i][1] == blocks[i + 1][0] for i in range(g - 1))
             assert max(b - a for a, b in blocks) - min(b - a for a, b in blocks) <= 1
+
+
+def test_column_starts_and_chunk_bounds():
+    """Host-side layout arithmetic of the peer-memory commit (no GPU call): column blocks tile the width, chunk bounds tile a
+    block in multiples of 8 columns, and hashing the chunk matrices in column order is hashing the dense row
+    (merkle_tree.rs:312-316 — the rule the chunk-major row blocks of p3gpu_commit_sharded_dev rely on)."""
+    import ctypes as C
+    from oracle import p3_oracle as O
+    from plonky3_b200 import _lib
+    from plonky3_b200.distributed import column_block, column_starts
+    L = _lib.load()
+    for width, world, align in [(100, 8, 8), (1312, 2, 8), (40, 8, 8), (11, 2, 1), (8, 4, 8)]:
+        st = column_starts(width, world, align)
+        assert st[0] == 0 and st[-1] == width and all(a <= b for a, b in zip(st, st[1:]))
+        assert [column_block(width, world, r, align) for r in range(world)] == list(zip(st[:-1], st[1:]))
+    for w_local in [0, 1, 7, 8, 64, 65, 100, 164, 656, 1312]:
+        buf = (C.c_size_t * (w_local // 8 + 3))()
+        n = L.p3gpu_shard_chunk_bounds(w_local, buf, len(buf))
+        b = [int(buf[i]) for i in range(n)]
+        assert n == (2 if 0 < w_local < 96 else len(b)) and b[0] == 0 and b[-1] == w_local and all(x < y for x, y in zip(b, b[1:]))   # w_local == 0: [0], no chunk
+        assert all(x % 8 == 0 for x in b[:-1])
+    be = OracleBackend()
+    m = O.random_matrix(F, 64, 164, seed=9)
+    buf = (C.c_size_t * 32)()
+    n = L.p3gpu_shard_chunk_bounds(164, buf, 32)
+    pieces = [np.ascontiguousarray(m[:, buf[i]:buf[i + 1]]) for i in range(n - 1) if buf[i + 1] > buf[i]]
+    dense, chunked = O.merkle_tree(be.hs, [m]), O.merkle_tree(be.hs, pieces)
+    assert all(np.array_equal(a, b) for a, b in zip(dense, chunked))
