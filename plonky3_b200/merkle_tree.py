@@ -46,6 +46,52 @@ def _host(x):
     return np.array(x, dtype=np.uint32)
 
 
+def _boundary_walk(indices, num_levels: int):
+    """The frontier walk both directions of the pruned multiproof share (merkle-tree/src/pruning.rs:116-176, binary schedule):
+    the sorted distinct leaf indices fold up level by level; a node whose sibling is not itself on the frontier needs that
+    sibling from the proof.  Yields (level, slot) in wire order — level 0 first, ascending parent index inside a level — where
+    `slot` is the position (in the caller's `indices`) of the smallest queried leaf under the node, whose full path holds the
+    sibling at `level`."""
+    first = {}
+    for slot, i in enumerate(indices):
+        first.setdefault(int(i), slot)
+    nodes = sorted(first.items())                                     # (node index at this level, lead slot)
+    for level in range(num_levels):
+        parents, k = [], 0
+        while k < len(nodes):
+            idx, lead = nodes[k]
+            if k + 1 < len(nodes) and nodes[k + 1][0] == (idx ^ 1):   # both children known: the verifier recomputes the parent
+                k += 2
+            else:
+                yield level, lead
+                k += 1
+            parents.append((idx >> 1, lead))
+        nodes = parents
+
+
+def prune_paths(indices, paths) -> np.ndarray:
+    """prune_paths (merkle-tree/src/pruning.rs:194-232): the minimal set of sibling digests of a batch of full paths.
+    `paths`: (n, levels, 8), sibling digests bottom-up for `indices[q]`.  Returns (k, 8) in the reference's wire order."""
+    paths = np.asarray(paths, dtype=np.uint32)
+    out = [paths[slot, level] for level, slot in _boundary_walk(indices, paths.shape[1])]
+    return np.array(out, dtype=np.uint32).reshape(len(out), 8)
+
+
+def restore_paths(indices, pruned, num_levels: int) -> np.ndarray:
+    """restore_paths (merkle-tree/src/pruning.rs:234-330): scatter the boundary digests back into the lead paths.  Positions
+    the amortised verifier recomputes itself stay zero.  Raises ValueError when the digest count does not match the frontier."""
+    pruned = np.asarray(pruned, dtype=np.uint32).reshape(-1, 8)
+    full = np.zeros((len(indices), num_levels, 8), dtype=np.uint32)
+    k = 0
+    for level, slot in _boundary_walk(indices, num_levels):
+        if k >= pruned.shape[0]:
+            raise ValueError("pruned proof is shorter than its frontier")
+        full[slot, level] = pruned[k]; k += 1
+    if k != pruned.shape[0]:
+        raise ValueError(f"pruned proof holds {pruned.shape[0]} digests, the frontier needs {k}")
+    return full
+
+
 class MerkleTreeMmcs:
     """MerkleTreeMmcs<P, PW, H, C, 2, 8>.
 
@@ -152,3 +198,11 @@ class MerkleTreeMmcs:
         for l in range(path_len):
             paths[:, l] = _host(layers[l])[(idx >> l) ^ 1]
         return openings, paths
+
+    # merkle-tree/src/mmcs/batch.rs:275-284, mmcs/mod.rs:276-428: the wire form of a multi-opening
+    def open_multi_batch_pruned(self, indices, prover_data: MerkleTree):
+        """Returns (opened_values[query][matrix] = row, pruned multiproof (k, 8)): the device gathers of `open_multi_batch`
+        followed by the host-side re-encoding `prune_paths`."""
+        openings, paths = self.open_multi_batch(indices, prover_data)
+        opened_values = [[openings[m][q] for m in range(len(openings))] for q in range(len(indices))]
+        return opened_values, prune_paths(indices, paths)

@@ -95,6 +95,14 @@ class Proof:
     commit_phase_openings: list                   # per FRI round: (log_arity, sibling values (n, arity-1, 4), paths)
     degree_bits: int
     timings_ms: dict = dc_field(default_factory=dict)
+    trace_next: Optional[np.ndarray] = None       # (width, 4) when the AIR reads the next row (uni-stark/src/proof.rs:52-56)
+    input_opening_indices: list = dc_field(default_factory=list)     # per input batch: the height-reduced query indices
+    commit_phase_indices: list = dc_field(default_factory=list)      # per FRI round: the opened group index of every query
+
+    def to_postcard(self) -> bytes:
+        """The reference's wire form (`postcard::to_allocvec(&proof)`, uni-stark/tests/fib_air.rs:401-412)."""
+        from .proof_io import proof_to_postcard
+        return proof_to_postcard(self)
 
 
 def get_log_num_quotient_chunks(air) -> int:
@@ -157,7 +165,8 @@ def prove(config: StarkConfig, air: VectorizedPoseidon2Air, trace, public_values
                  quotient_chunks=[v[0] for v in opened_values[1]], commit_phase_commits=fri["commits"],
                  commit_pow_witnesses=fri["pow_witnesses"], final_poly=fri["final_poly"], query_pow_witness=fri["query_pow_witness"],
                  query_indices=fri["indices"], input_openings=fri["input_openings"], commit_phase_openings=fri["commit_phase_openings"],
-                 degree_bits=log_degree, timings_ms=T)
+                 degree_bits=log_degree, timings_ms=T, input_opening_indices=fri["input_opening_indices"],
+                 commit_phase_indices=fri["commit_phase_indices"])
 
 
 def prove_fri(pcs: TwoAdicFriPcs, inputs: list, challenger: DuplexChallenger, prover_data_with_opening_points: list) -> dict:
@@ -179,15 +188,17 @@ def prove_fri(pcs: TwoAdicFriPcs, inputs: list, challenger: DuplexChallenger, pr
     indices = [challenger.sample_bits(log_global_max_height) for _ in range(params.num_queries)]     # extra_query_index_bits = 0
     t0 = time.perf_counter()
     # open_inputs (:380-417): every committed batch at the (height-reduced) query indices
-    input_openings = []
+    input_openings, input_opening_indices, commit_phase_indices = [], [], []
     for data, _ in prover_data_with_opening_points:
         log_max_height = _log2_strict(pcs.mmcs.get_max_height(data))
         reduced = [i >> (log_global_max_height - log_max_height) for i in indices]
         input_openings.append(pcs.mmcs.open_multi_batch(reduced, data))
+        input_opening_indices.append(reduced)
     # answer_queries (:308-378)
     commit_phase_openings, cur = [], list(indices)
     for la, data in zip(res.log_arities, res.data):
         group = [i >> la for i in cur]
+        commit_phase_indices.append(group)
         rows, paths = params.mmcs.open_multi_batch(group, data)
         opened = rows[0].reshape(len(cur), 1 << la, 4)
         keep = np.array([[j for j in range(1 << la) if j != (i & ((1 << la) - 1))] for i in cur], dtype=np.int64)
@@ -197,4 +208,4 @@ def prove_fri(pcs: TwoAdicFriPcs, inputs: list, challenger: DuplexChallenger, pr
     torch.cuda.synchronize(); T["query phase"] = (time.perf_counter() - t0) * 1e3
     return {"commits": res.commits, "pow_witnesses": res.pow_witnesses, "final_poly": res.final_poly, "query_pow_witness": pow_witness,
             "indices": indices, "input_openings": input_openings, "commit_phase_openings": commit_phase_openings, "log_arities": res.log_arities,
-            "timings_ms": T}
+            "input_opening_indices": input_opening_indices, "commit_phase_indices": commit_phase_indices, "timings_ms": T}

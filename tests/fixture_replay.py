@@ -163,8 +163,18 @@ def _c_rows(arr):  # Montgomery matrix -> canonical python rows
     return [[from_m(int(v)) for v in r] for r in np.asarray(arr)]
 
 
+def _commit(backend, mats):
+    """(cap, prover data or None).  Backends with `commit_data`/`open_multi` also replay the query phase."""
+    if hasattr(backend, "commit_data"):
+        return backend.commit_data(mats)
+    return backend.commit(mats), None
+
+
 def replay(backend):
-    """Returns a dict with the same keys/encoding (Montgomery u32) as the golden JSON."""
+    """Returns a dict with the same keys/encoding (Montgomery u32) as the golden JSON.  With a backend that keeps prover data
+    (`commit_data(mats) -> (cap, data)`, `open_multi(data, indices) -> (rows per matrix (n, w), full sibling paths (n, L, 8))`)
+    the query phase is replayed too (fri/src/prover.rs:103-160,308-417) and the whole proof is returned in wire form under
+    "postcard_hex" (plonky3_b200.proof_io on a plonky3_b200.uni_stark.Proof)."""
     rc_i, rc_t, rc_p = fixture_constants()
     perm = PyPerm(rc_i, rc_t, rc_p)
     w8 = gen(3); w32 = gen(5); w8i = inv(w8)
@@ -173,7 +183,7 @@ def replay(backend):
 
     # --- pcs.commit(trace): coset LDE onto GENERATOR*K (blowup 4), bit-reversed rows, Merkle commit
     trace_lde_m = backend.lde(_m_arr(rows), 2, to_m(GEN))           # two_adic_pcs.rs:300-324
-    trace_cap = backend.commit([trace_lde_m])
+    trace_cap, trace_data = _commit(backend, [trace_lde_m])
     lde = _c_rows(trace_lde_m)
     trace_root = [from_m(int(v)) for v in np.asarray(trace_cap)[0]]
 
@@ -203,7 +213,7 @@ def replay(backend):
 
     # --- pcs.commit_quotient: evals on GENERATOR*H -> coset_lde_batch(shift = 1) -> GENERATOR*K
     quot_lde_m = backend.lde(_m_arr(Q), 2, to_m(1))                  # two_adic_pcs.rs:326-345
-    quot_cap = backend.commit([quot_lde_m])
+    quot_cap, quot_data = _commit(backend, [quot_lde_m])
     qlde = _c_rows(quot_lde_m)
     quot_root = [from_m(int(v)) for v in np.asarray(quot_cap)[0]]
     for v in quot_root: ch.observe(v)
@@ -245,7 +255,7 @@ def replay(backend):
 
     # --- FRI commit phase round 0: commit (16 x 2 EF = 16 x 8 base), grind, beta, fold   (fri/src/prover.rs:219-266)
     ro_m = _m_arr(ro)                                                 # (32, 4)
-    fri_cap = backend.commit([ro_m.reshape(16, 8)])
+    fri_cap, fri_data = _commit(backend, [ro_m.reshape(16, 8)])
     fri_root = [from_m(int(v)) for v in np.asarray(fri_cap)[0]]
     for v in fri_root: ch.observe(v)
     for cand in range(P):                                             # grind(1): smallest witness (serial build)
@@ -259,7 +269,39 @@ def replay(backend):
     final = [[sum(f4[j][c] * pow(w4i, i * j, P) for j in range(4)) * inv(4) % P for c in range(4)] for i in range(4)]
 
     mm = lambda rows_: [[to_m(v) for v in r] for r in rows_]
+    query = {}
+    if trace_data is not None:
+        # --- query phase: bind final poly + arity schedule, grind, sample the indices, open everything   (fri/src/prover.rs:103-160)
+        for co in final:
+            for v in co: ch.observe(v)
+        ch.observe(1)                                                 # log_arity of the single round
+        for cand in range(P):                                         # grind(query_proof_of_work_bits = 1)
+            c2 = copy.deepcopy(ch); c2.observe(cand)
+            if c2.sample() & 1 == 0:
+                qwit = cand; ch = c2; break
+        indices = [ch.sample() & 31 for _ in range(2)]                # sample_bits(log_global_max_height = 5)
+        from plonky3_b200.merkle_tree import prune_paths
+        from plonky3_b200.uni_stark import Proof
+        input_openings = [backend.open_multi(trace_data, indices), backend.open_multi(quot_data, indices)]
+        group = [i >> 1 for i in indices]
+        rows, paths = backend.open_multi(fri_data, group)
+        opened = np.asarray(rows[0], dtype=np.uint32).reshape(2, 2, 4)
+        siblings = np.array([[opened[q][(i & 1) ^ 1]] for q, i in enumerate(indices)], dtype=np.uint32)     # (2, arity - 1, 4)
+        proof = Proof(trace_commit=np.asarray(trace_cap), quotient_commit=np.asarray(quot_cap), trace_local=_m_arr(y1),
+                      quotient_chunks=[_m_arr(y3)], commit_phase_commits=[np.asarray(fri_cap)], commit_pow_witnesses=[to_m(wit)],
+                      final_poly=_m_arr(final), query_pow_witness=to_m(qwit), query_indices=indices, input_openings=input_openings,
+                      commit_phase_openings=[(1, siblings, paths)], degree_bits=3, trace_next=_m_arr(y2),
+                      input_opening_indices=[indices, indices], commit_phase_indices=[group])
+        ints = lambda a: [[int(v) for v in r] for r in np.asarray(a).reshape(-1, np.asarray(a).shape[-1])]
+        query = {
+            "query_pow_witness": to_m(qwit),
+            "input_openings": [{"opened_values": [[[int(v) for v in m[q]] for m in r] for q in range(2)], "proof": ints(prune_paths(indices, pth))}
+                               for r, pth in input_openings],
+            "commit_phase_openings": [{"log_arity": 1, "sibling_values": [ints(siblings[q]) for q in range(2)], "proof": ints(prune_paths(group, paths))}],
+            "postcard_hex": proof.to_postcard().hex(),
+        }
     return {
+        **query,
         "trace_cap": [[to_m(v) for v in trace_root]],
         "quotient_cap": [[to_m(v) for v in quot_root]],
         "trace_local": mm(y1), "trace_next": mm(y2), "quotient_chunks": [mm(y3)],

@@ -191,6 +191,28 @@ def prove(air, perm16, perm24, inputs, cap_height=3, log_blowup=1, max_log_arity
             "log_n": log_n}
 
 
+def to_wire_proof(pr):
+    """The replay's proof as a plonky3_b200.uni_stark.Proof (host-side container; `.to_postcard()` is the reference's wire form)."""
+    from plonky3_b200.uni_stark import Proof
+    cp_idx, cur = [], list(pr["indices"])
+    for la in pr["log_arities"]:
+        cur = [i >> la for i in cur]
+        cp_idx.append(cur)
+    return Proof(trace_commit=pr["trace_cap"], quotient_commit=pr["quotient_cap"], trace_local=pr["trace_local"],
+                 quotient_chunks=pr["quotient_chunks"], commit_phase_commits=pr["commit_phase_commits"],
+                 commit_pow_witnesses=[0] * len(pr["commit_phase_commits"]), final_poly=pr["final_poly"],
+                 query_pow_witness=pr["query_pow_witness"], query_indices=pr["indices"], input_openings=pr["input_openings"],
+                 commit_phase_openings=pr["commit_phase_openings"], degree_bits=pr["log_n"],
+                 input_opening_indices=[pr["indices"]] * len(pr["input_openings"]), commit_phase_indices=cp_idx)
+
+
+def verifier_config(perm16, perm24, cap_height=3, log_blowup=1, max_log_arity=3, num_queries=100, query_pow_bits=16):
+    """tests/stark_verify.py configuration of the example binary's StarkConfig (examples/src/proofs.rs, new_benchmark_high_arity)."""
+    return dict(hasher=O.poseidon2_hasher(perm24, perm16), challenger_perm=perm24, challenger_width=24, challenger_rate=16,
+                log_blowup=log_blowup, log_final_poly_len=0, max_log_arity=max_log_arity, num_queries=num_queries,
+                commit_pow_bits=0, query_pow_bits=query_pow_bits)
+
+
 # ------------------------------------------------------------------------------------------------ verifier identity (plain integers)
 RINV = pow(1 << 32, P - 2, P)
 W = 3

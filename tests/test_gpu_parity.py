@@ -344,6 +344,8 @@ class GpuBackend:
     def lde(self, mat, added_bits, shift): return self.dft.coset_lde_batch(mat, added_bits, shift).bit_reverse_rows()
     def commit(self, mats): return self.mmcs.commit(mats)[0]
     def fold(self, vec, log_arity, beta): return self.folding.fold_matrix(beta, log_arity, vec)
+    def commit_data(self, mats): return self.mmcs.commit([dev(m) for m in mats])            # device-resident prover data
+    def open_multi(self, data, indices): return self.mmcs.open_multi_batch(indices, data)   # csrc/query.cu gathers
 
 
 class GpuOpenBackend(GpuBackend):
@@ -405,9 +407,11 @@ def test_open_worst_case_accumulators(gpu):
 
 
 def test_fixture_replay_on_gpu(gpu):
-    """The reference's committed proof (uni_stark_two_adic_v1.postcard) is reproduced with LDE, Merkle and FRI fold on the GPU."""
+    """The reference's committed proof (uni_stark_two_adic_v1.postcard) is reproduced with LDE, Merkle, FRI fold and the query
+    gathers on the GPU — every field, and the serialised proof byte for byte (`postcard_hex`, 1115 bytes)."""
     gold = json.loads((GOLD / "uni_stark_two_adic_v1.json").read_text())
     got = FR.replay(GpuBackend(gpu))
+    assert "postcard_hex" in got and "input_openings" in got
     for k, v in got.items():
         assert v == gold[k], k
 

@@ -79,6 +79,13 @@ def test_prove_matches_cpu_replay(setup, log_n, num_queries, pow_bits):
     # the GPU proof satisfies the verifier's identity as well (same check on the GPU's own opened values)
     mine = dict(exp, trace_local=proof.trace_local, quotient_chunks=proof.quotient_chunks)
     assert R.verify_constraints_at_zeta(oair, mine)
+    # wire form (postcard, pruned multiproofs): same bytes as the replay's, and the restated reference verifier — the one that
+    # accepts the reference's own proof fixture (tests/test_oracle.py) — accepts what the GPU wrote
+    import stark_verify as V
+    from plonky3_b200.proof_io import proof_from_postcard
+    raw = proof.to_postcard()
+    assert raw == R.to_wire_proof(exp).to_postcard()
+    V.verify(V.Fld(f.id), R.verifier_config(o16, o24, num_queries=num_queries, query_pow_bits=pow_bits), V.poseidon2_air(oair), proof_from_postcard(raw))
 
 
 def test_challenger_matches_oracle(setup):
