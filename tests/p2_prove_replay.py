@@ -10,7 +10,9 @@ Parity anchor: the generic flow (LDE layout, MMCS, challenger, alpha ordering, o
 the reference's committed proof fixture (tests/fixture_replay.py); the AIR-specific parts (trace columns, constraint order) follow
 poseidon2-air/src/{columns,generation,air,vectorized}.rs and are additionally checked by `verify_constraints_at_zeta`, a restatement
 of the verifier's identity C(zeta) / Z_H(zeta) = Q(zeta) (uni-stark/src/verifier.rs:98-220) in plain Python integers.
-PARITY UNPINNED by a reference artifact for this AIR: the reference holds no proof fixture of prove_prime_field_31.
+PARITY UNPINNED by a reference artifact for this AIR: the reference holds no proof fixture of prove_prime_field_31.  The proof in
+wire form (`to_wire_proof(...).to_postcard()`) is accepted by tests/stark_verify.py, the restated verifier that accepts the
+reference's own committed proof.
 """
 import numpy as np
 
