@@ -628,8 +628,12 @@ int32_t p3gpu_commit_sharded_dev(p3gpu_ctx *ctx, int field, int hash, const p3gp
     P3_CHECK(d_evals_local || w_local == 0, P3GPU_EINVAL, "null argument");
     const size_t H = h << log_blowup, rows = H / world;
     const double tmo = grp->timeout_s > 0 ? grp->timeout_s : 20.0;
-    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
-    if (phase_ms) for (auto &e : ev) P3_CUDA(cudaEventCreate(&e));
+    struct PhaseEvents {                             // destroyed on every return path
+        cudaEvent_t e[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+        ~PhaseEvents() { for (auto &x : e) if (x) cudaEventDestroy(x); }
+    } pe;
+    cudaEvent_t *ev = pe.e;
+    if (phase_ms) for (auto &e : pe.e) P3_CUDA(cudaEventCreate(&e));
     auto mark = [&](int k) -> int32_t { if (phase_ms) P3_CUDA(cudaEventRecord(ev[k], ctx->stream)); return P3GPU_OK; };
     // the row blocks may still be read by the previous commit's hashing on some rank: nobody starts overwriting them before
     // every rank has entered this call
@@ -687,10 +691,8 @@ int32_t p3gpu_commit_sharded_dev(p3gpu_ctx *ctx, int field, int hash, const p3gp
     }
     P3_TRY(mark(4));
     P3_CUDA(cudaStreamSynchronize(ctx->stream));
-    if (phase_ms) {
+    if (phase_ms)
         for (int k = 0; k < 4; k++) P3_CUDA(cudaEventElapsedTime(&phase_ms[k], ev[k], ev[k + 1]));
-        for (auto &e : ev) cudaEventDestroy(e);
-    }
     return P3GPU_OK;
 }
 
