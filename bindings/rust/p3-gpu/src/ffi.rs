@@ -6,6 +6,11 @@ pub struct P3GpuCtx {
     _private: [u8; 0],
 }
 
+#[repr(C)]
+pub struct P3GpuChallenger {
+    _private: [u8; 0],
+}
+
 pub const P3GPU_BABY_BEAR: i32 = 0;
 pub const P3GPU_KOALA_BEAR: i32 = 1;
 pub const P3GPU_DFT: i32 = 0;
@@ -91,6 +96,41 @@ unsafe extern "C" {
                                     cap_height: c_uint, d_sub_layers: *mut u32, layer_lens: *mut usize, n_layers: *mut usize, h_cap: *mut u32,
                                     cap_len: *mut usize, phase_ms: *mut f32) -> i32;
     pub fn p3gpu_shard_chunk_bounds(w_local: usize, bounds: *mut usize, max_bounds: usize) -> usize;
+    pub fn p3gpu_memset_dev(ctx: *mut P3GpuCtx, dptr: *mut c_void, value: c_int, bytes: usize) -> i32;
+    pub fn p3gpu_peer_allgather_dev(ctx: *mut P3GpuCtx, grp: *const P3GpuPeerGroup, table_offset_bytes: usize, d_src: *const u32, words: usize) -> i32;
+    pub fn p3gpu_coset_lde_batch_sharded_dev(ctx: *mut P3GpuCtx, field: c_int, grp: *const P3GpuPeerGroup, d_in: *const u32, h: usize,
+                                             w_local: usize, added_bits: c_uint, shift: u32, w_total: usize, col_off: usize) -> i32;
+
+    // streams, counters
+    pub fn p3gpu_ctx_set_stream(ctx: *mut P3GpuCtx, cuda_stream: *mut c_void) -> i32;
+    pub fn p3gpu_ctx_use_own_stream(ctx: *mut P3GpuCtx) -> i32;
+    pub fn p3gpu_launch_count(ctx: *const P3GpuCtx) -> u64;
+
+    // bare permutations, tree above given digests, bench-only commit phase with pre-drawn betas
+    pub fn p3gpu_poseidon2_permute_dev(ctx: *mut P3GpuCtx, field: c_int, width: c_int, d_states: *mut u32, n: usize) -> i32;
+    pub fn p3gpu_keccak_f_dev(ctx: *mut P3GpuCtx, d_states: *mut u64, n: usize) -> i32;
+    pub fn p3gpu_merkle_from_digests_dev(ctx: *mut P3GpuCtx, field: c_int, hash: c_int, d_digests: *const u32, n: usize, d_layers: *mut u32,
+                                         layer_lens: *mut usize, n_layers: *mut usize) -> i32;
+    pub fn p3gpu_fri_commit_phase_dev(ctx: *mut P3GpuCtx, field: c_int, hash: c_int, d_vec: *mut u32, len: usize, log_blowup: c_uint,
+                                      log_final_poly_len: c_uint, max_log_arity: c_uint, cap_height: c_uint, betas: *const u32, n_betas: usize,
+                                      h_caps: *mut u32, cap_lens: *mut usize, log_arities: *mut c_uint, n_rounds: *mut usize, h_final: *mut u32) -> i32;
+
+    // Poseidon2 AIR (poseidon2-air): trace generation and quotient values
+    pub fn p3gpu_p2air_set_constants(ctx: *mut P3GpuCtx, field: c_int, beginning_full: *const u32, partial: *const u32, rounds_p: c_int,
+                                     ending_full: *const u32) -> i32;
+    pub fn p3gpu_p2air_columns(rounds_p: c_int) -> usize;
+    pub fn p3gpu_p2air_generate_trace_dev(ctx: *mut P3GpuCtx, field: c_int, d_inputs: *const u32, n_perms: usize, d_trace: *mut u32) -> i32;
+    pub fn p3gpu_p2air_quotient_dev(ctx: *mut P3GpuCtx, field: c_int, vector_len: c_int, d_lde: *const u32, log_lde_height: c_uint,
+                                    log_trace_height: c_uint, alpha: *const u32, d_quotient: *mut u32) -> i32;
+
+    // DuplexChallenger with device-resident state
+    pub fn p3gpu_challenger_new(ctx: *mut P3GpuCtx, field: c_int, width: c_int, rate: c_int, out: *mut *mut P3GpuChallenger) -> i32;
+    pub fn p3gpu_challenger_free(ctx: *mut P3GpuCtx, ch: *mut P3GpuChallenger);
+    pub fn p3gpu_challenger_clone(ctx: *mut P3GpuCtx, src: *const P3GpuChallenger, out: *mut *mut P3GpuChallenger) -> i32;
+    pub fn p3gpu_challenger_observe_dev(ctx: *mut P3GpuCtx, ch: *mut P3GpuChallenger, d_values: *const u32, n: usize) -> i32;
+    pub fn p3gpu_challenger_observe(ctx: *mut P3GpuCtx, ch: *mut P3GpuChallenger, h_values: *const u32, n: usize) -> i32;
+    pub fn p3gpu_challenger_sample(ctx: *mut P3GpuCtx, ch: *mut P3GpuChallenger, h_out: *mut u32, n: usize) -> i32;
+    pub fn p3gpu_challenger_grind(ctx: *mut P3GpuCtx, ch: *mut P3GpuChallenger, bits: c_uint, witness: *mut u32) -> i32;
 }
 
 /// The reference's prover-side trait methods have no `Result`: shape violations panic (`log2_strict_usize`,

@@ -26,6 +26,16 @@ def test_library_exports_every_declared_symbol():
     assert sorted(_lib.EXPORTS) == declared
 
 
+def test_rust_ffi_declares_every_header_symbol():
+    """bindings/rust/p3-gpu/src/ffi.rs (source only: no Rust toolchain in this image) must stay in step with include/p3gpu.h."""
+    import re
+    header = (ROOT / "include" / "p3gpu.h").read_text()
+    ffi = (ROOT / "bindings" / "rust" / "p3-gpu" / "src" / "ffi.rs").read_text()
+    declared = set(re.findall(r"\b(p3gpu_[a-z0-9_]+)\s*\(", header))
+    bound = set(re.findall(r"fn (p3gpu_[a-z0-9_]+)", ffi))
+    assert declared == bound, (sorted(declared - bound), sorted(bound - declared))
+
+
 def test_no_cpu_fallback():
     if torch.cuda.is_available():
         pytest.skip("device present")
