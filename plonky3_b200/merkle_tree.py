@@ -92,6 +92,75 @@ def restore_paths(indices, pruned, num_levels: int) -> np.ndarray:
     return full
 
 
+class MerkleTreeError(Exception):
+    """merkle-tree/src/mmcs/mod.rs MerkleTreeError (WrongBatchSize, WrongWidth, WrongHeight, IndexOutOfBounds, CapMismatch, ...)."""
+
+
+def verify_multi_batch_with(hash_rows, compress_pairs, cap, dims, indices, opened_values, pruned):
+    """verify_batch_pruned (merkle-tree/src/mmcs/mod.rs:430-): ONE amortised check of all queries of a batch.  Every distinct
+    opened leaf is hashed once; the frontier folds up level by level — a sibling comes from the multiproof only where no queried
+    leaf covers it, otherwise it was just computed; shorter matrices are injected where the level reaches their height
+    (compress(node, hash(rows)), merkle_tree.rs:348-); every proof digest must be consumed and every surviving node must equal its
+    cap entry.  `hash_rows((n, w) words) -> (n, 8)` and `compress_pairs((n, 8), (n, 8)) -> (n, 8)` do the hashing — one call per
+    level for all queries — so the caller decides where it runs.  `dims`: [(width, height)] per matrix; `opened_values[q][m]`."""
+    def req(cond, msg):
+        if not cond:
+            raise MerkleTreeError(msg)
+    cap = np.asarray(cap, dtype=np.uint32).reshape(-1, 8)
+    log_cap = cap.shape[0].bit_length() - 1
+    req(len(dims) > 0 and cap.shape[0] == 1 << log_cap, "wrong batch size")
+    logs = [_log2_ceil(int(h)) for _, h in dims]
+    log_max = max(logs)
+    req(log_cap <= log_max and min(logs) >= log_cap, "matrix heights do not fit the cap")
+    req(len(opened_values) == len(indices), "wrong batch size")
+    by_level = {}
+    for m, lg in enumerate(logs):
+        by_level.setdefault(lg, []).append(m)
+    rows_at = [dict() for _ in dims]                                  # per matrix: reduced index -> opened row (must be unique)
+    rep = {}
+    for q, (i, rows) in enumerate(zip(indices, opened_values)):
+        req(0 <= int(i) < (1 << log_max), "index out of bounds")
+        req(len(rows) == len(dims), "wrong batch size")
+        for m, (row, (w, _)) in enumerate(zip(rows, dims)):
+            row = np.asarray(row, dtype=np.uint32).ravel()
+            req(row.size == w, "wrong width")
+            known = rows_at[m].setdefault(int(i) >> (log_max - logs[m]), row)
+            req(known is row or np.array_equal(known, row), "two openings of one row disagree")
+        rep.setdefault(int(i), q)
+    nodes = sorted(rep)
+
+    def level_digests(lg, node_ids):
+        ms = by_level[lg]
+        return hash_rows(np.stack([np.concatenate([rows_at[m][nid] for m in ms]) for nid in node_ids]))
+
+    dig = np.asarray(level_digests(log_max, nodes), dtype=np.uint32).reshape(len(nodes), 8)
+    pruned = np.asarray(pruned, dtype=np.uint32).reshape(-1, 8)
+    k = 0
+    for lvl in range(log_max, log_cap, -1):
+        left, right, parents, j = [], [], [], 0
+        while j < len(nodes):
+            idx = nodes[j]
+            if j + 1 < len(nodes) and nodes[j + 1] == (idx ^ 1):
+                left.append(dig[j]); right.append(dig[j + 1]); j += 2
+            else:
+                req(k < pruned.shape[0], "multiproof is shorter than its frontier")
+                sib = pruned[k]; k += 1
+                if idx & 1:
+                    left.append(sib); right.append(dig[j])
+                else:
+                    left.append(dig[j]); right.append(sib)
+                j += 1
+            parents.append(idx >> 1)
+        dig = np.asarray(compress_pairs(np.array(left, dtype=np.uint32), np.array(right, dtype=np.uint32)), dtype=np.uint32).reshape(len(parents), 8)
+        nodes = parents
+        if (lvl - 1) in by_level:                                     # inject the matrices of this height
+            inj = np.asarray(level_digests(lvl - 1, nodes), dtype=np.uint32).reshape(len(nodes), 8)
+            dig = np.asarray(compress_pairs(dig, inj), dtype=np.uint32).reshape(len(nodes), 8)
+    req(k == pruned.shape[0], "multiproof holds digests the frontier does not use")
+    for idx, d in zip(nodes, dig):
+        req(np.array_equal(cap[idx], d), "cap mismatch")
+
+
 class MerkleTreeMmcs:
     """MerkleTreeMmcs<P, PW, H, C, 2, 8>.
 
@@ -198,6 +267,30 @@ class MerkleTreeMmcs:
         for l in range(path_len):
             paths[:, l] = _host(layers[l])[(idx >> l) ^ 1]
         return openings, paths
+
+    # ---- verifier side: batch hashing on the device
+    def hash_rows(self, rows):
+        """Leaf digests of n rows ((n, w) Montgomery words) — the leaf kernel on an n-row matrix."""
+        rows = np.ascontiguousarray(rows, dtype=np.uint32)
+        for p in self.perms:
+            p.upload(self.gpu)
+        return _host(self.gpu.merkle_commit(self.field.id, self.hash_kind, [rows])[0])[: rows.shape[0]]
+
+    def compress_pairs(self, left, right):
+        """compress([left[i], right[i]]) for n pairs: the node kernel on the interleaved digests (one tree level)."""
+        left = np.asarray(left, dtype=np.uint32).reshape(-1, 8)
+        inter = np.empty((2 * left.shape[0], 8), dtype=np.uint32)
+        inter[0::2] = left; inter[1::2] = np.asarray(right, dtype=np.uint32).reshape(-1, 8)
+        for p in self.perms:
+            p.upload(self.gpu)
+        import torch
+        dev = torch.from_numpy(inter.view(np.int32)).to(f"cuda:{self.gpu.device}")
+        return _host(self.gpu.merkle_from_digests(self.field.id, self.hash_kind, dev)[1])[: left.shape[0]]
+
+    # commit/src/mmcs.rs:190-199, merkle-tree/src/mmcs/batch.rs:286-296
+    def verify_multi_batch(self, commit, dimensions, indices, opened_values, proof):
+        """Raises MerkleTreeError.  `dimensions`: [(width, height)]; `proof`: the pruned multiproof (k, 8)."""
+        verify_multi_batch_with(self.hash_rows, self.compress_pairs, commit, dimensions, indices, opened_values, proof)
 
     # merkle-tree/src/mmcs/batch.rs:275-284, mmcs/mod.rs:276-428: the wire form of a multi-opening
     def open_multi_batch_pruned(self, indices, prover_data: MerkleTree):

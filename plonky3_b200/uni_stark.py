@@ -49,6 +49,8 @@ class VectorizedPoseidon2Air:
 
     def _upload(self):
         c = self.constants
+        if self.gpu is None:                     # verifier-only use: the constraint folder below is host code
+            return
         self.gpu.p2air_set_constants(self.field.id, c.beginning_full_round_constants, c.partial_round_constants, c.ending_full_round_constants)
 
     def width(self) -> int:                      # BaseAir::width (vectorized.rs)
@@ -57,13 +59,72 @@ class VectorizedPoseidon2Air:
     def max_constraint_degree(self) -> int:      # air.rs:151-160 for (3, 0)
         return 3
 
+    def num_public_values(self) -> int: return 0
+    def main_next_row_columns(self): return []   # no transition constraints: the next row is never opened (verifier.rs:431-440)
+
+    def eval_folded_constraints(self, e, local, nxt, public_values, is_first_row, is_last_row, is_transition, alpha):
+        """The verifier's constraint folder (uni-stark/src/folder.rs VerifierConstraintFolder: acc = acc * alpha + c per
+        assert_zero) over the opened row at zeta, scalar host code on canonical EF4 values (`e`: verifier.Ext).  Constraint order =
+        poseidon2-air/src/air.rs eval: per permutation the committed post-state of every full round (16 each) and the S-box output
+        of every partial round; degree-3 S-box without registers."""
+        f, P = self.field, self.field.P
+        c = self.constants
+        beg = [[f.from_monty(int(v)) for v in r] for r in np.asarray(c.beginning_full_round_constants).reshape(4, 16)]
+        end = [[f.from_monty(int(v)) for v in r] for r in np.asarray(c.ending_full_round_constants).reshape(4, 16)]
+        part = [f.from_monty(int(v)) for v in np.asarray(c.partial_round_constants).ravel()]
+        ip = lambda k: pow(pow(2, k, P), P - 2, P)
+        # internal diagonal of Poseidon2KoalaBear<16> (koala-bear/src/poseidon2.rs:410-428)
+        v16 = [P - 2, 1, 2, ip(1), 3, 4, P - ip(1), P - 3, P - 4, ip(8), ip(3), ip(24), P - ip(8), P - ip(3), P - ip(4), P - ip(24)]
+        add, sc, mul = e.add, e.scale, e.mul
+
+        def mat4(x):
+            a, b, cc, d = x
+            return [add(add(sc(a, 2), sc(b, 3)), add(cc, d)), add(add(a, sc(b, 2)), add(sc(cc, 3), d)),
+                    add(add(a, b), add(sc(cc, 2), sc(d, 3))), add(add(sc(a, 3), b), add(cc, sc(d, 2)))]
+
+        def mds(s):
+            s = sum((mat4(s[i:i + 4]) for i in range(0, 16, 4)), [])
+            t = [[0, 0, 0, 0] for _ in range(4)]
+            for i in range(16):
+                t[i % 4] = add(t[i % 4], s[i])
+            return [add(s[i], t[i % 4]) for i in range(16)]
+
+        cube = lambda x: mul(mul(x, x), x)
+        cols = 144 + self.rounds_p
+        acc = [0, 0, 0, 0]
+        for v in range(self.vector_len):
+            col = local[v * cols:(v + 1) * cols]
+            s = mds(col[:16]); k = 16
+            for rc in beg:
+                s = mds([cube(add(s[i], e.base(rc[i]))) for i in range(16)])
+                for i in range(16):
+                    acc = add(mul(acc, alpha), e.sub(s[i], col[k + i])); s[i] = col[k + i]
+                k += 16
+            for r in range(self.rounds_p):
+                x = cube(add(s[0], e.base(part[r])))
+                acc = add(mul(acc, alpha), e.sub(x, col[k])); s[0] = col[k]; k += 1
+                t = [0, 0, 0, 0]
+                for i in range(16):
+                    t = add(t, s[i])
+                s = [add(sc(s[i], v16[i]), t) for i in range(16)]
+            for rc in end:
+                s = mds([cube(add(s[i], e.base(rc[i]))) for i in range(16)])
+                for i in range(16):
+                    acc = add(mul(acc, alpha), e.sub(s[i], col[k + i])); s[i] = col[k + i]
+                k += 16
+        return acc
+
     def generate_trace_rows(self, inputs_dev):
         """generate_vectorized_trace_rows (generation.rs:14-70): (n_perms, 16) device inputs -> (n_perms / 8, 1312) device trace."""
+        if self.gpu is None:
+            raise _lib.P3GpuError("trace generation needs a GPU context (no CPU fallback)")
         self._upload()
         return self.gpu.p2air_generate_trace(self.field.id, inputs_dev, self.vector_len)
 
     def quotient_values(self, trace_lde_dev, log_degree: int, alpha):
         """uni-stark/src/prover.rs:462-827 on the committed LDE (natural order over the quotient domain)."""
+        if self.gpu is None:
+            raise _lib.P3GpuError("quotient evaluation needs a GPU context (no CPU fallback)")
         self._upload()
         return self.gpu.p2air_quotient(self.field.id, trace_lde_dev, log_degree, alpha, self.vector_len)
 
@@ -109,6 +170,12 @@ def get_log_num_quotient_chunks(air) -> int:
     """uni-stark/src/symbolic.rs get_log_num_quotient_chunks: log2_ceil(max(constraint_degree, 2) - 1) (non-ZK)."""
     d = max(air.max_constraint_degree(), 2)
     return max(d - 2, 0).bit_length()
+
+
+def verify(config: StarkConfig, air, proof, public_values=()):
+    """uni-stark/src/verifier.rs:282-295.  Raises verifier.VerificationError."""
+    from .verifier import verify as _verify
+    return _verify(config, air, proof, public_values)
 
 
 def prove(config: StarkConfig, air: VectorizedPoseidon2Air, trace, public_values=()) -> Proof:

@@ -410,3 +410,64 @@ def poseidon2_air(air, vec=8):
                 k += 16
         return acc
     return {"width": vec * (144 + air.rounds_p), "main_next": False, "log_quotient_chunks": 1, "num_public_values": 0, "constraints": constraints}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Oracle-backed stand-ins that let the PRODUCT verifier (plonky3_b200/verifier.py) run on the CPU: same verifier code as on the
+# GPU, with hashing and the transcript permutation done by the C oracle instead of the device.  Test infrastructure.
+class OracleMmcs:
+    """The verifier-side surface of plonky3_b200.merkle_tree.MerkleTreeMmcs (hash_rows / compress_pairs / verify_multi_batch)."""
+
+    def __init__(self, hasher):
+        self.hs = hasher
+
+    def hash_rows(self, rows): return np.array([O.hash_row(self.hs, r) for r in np.asarray(rows, dtype=np.uint32)], dtype=np.uint32)
+
+    def compress_pairs(self, left, right):
+        return np.array([O.compress(self.hs, l, r) for l, r in zip(np.asarray(left, dtype=np.uint32), np.asarray(right, dtype=np.uint32))], dtype=np.uint32)
+
+    def verify_multi_batch(self, commit, dims, indices, opened_values, proof):
+        from plonky3_b200.merkle_tree import verify_multi_batch_with
+        verify_multi_batch_with(self.hash_rows, self.compress_pairs, commit, dims, indices, opened_values, proof)
+
+
+class OracleDuplexChallenger:
+    """The surface of plonky3_b200.challenger.DuplexChallenger the verifier uses, on the Challenger above (Montgomery words in/out)."""
+
+    def __init__(self, fld, perm, width, rate):
+        self.f, self.ch = fld, Challenger(fld, perm, width, rate)
+
+    def observe(self, word): self.ch.observe(self.f.c(word))
+    def observe_canonical(self, x): self.ch.observe(x)
+    def observe_slice(self, words): self.ch.observe_words(words)
+    def sample_algebra_element(self): return np.array([self.f.m(v) for v in self.ch.sample_ef()], dtype=np.uint32)
+    def sample_bits(self, bits): return self.ch.sample_bits(bits)
+
+
+def product_config(field, cfg):
+    """A StarkConfig-shaped object for plonky3_b200.verifier.verify from the dict configuration used above."""
+    from types import SimpleNamespace
+    from plonky3_b200.fri import FriParameters
+    mmcs = OracleMmcs(cfg["hasher"])
+    fri = FriParameters(cfg["log_blowup"], cfg["log_final_poly_len"], cfg["max_log_arity"], cfg["num_queries"], cfg["commit_pow_bits"],
+                        cfg["query_pow_bits"], mmcs)
+    fld = Fld(field.id)
+    return SimpleNamespace(pcs=SimpleNamespace(fri=fri, mmcs=mmcs, dft=SimpleNamespace(field=field)),
+                           initialise_challenger=lambda: OracleDuplexChallenger(fld, cfg["challenger_perm"], cfg["challenger_width"], cfg["challenger_rate"]))
+
+
+class FibonacciAir:
+    """uni-stark/tests/fib_air.rs:33-75 in the AIR surface plonky3_b200.verifier.verify expects."""
+    def width(self): return 2
+    def num_public_values(self): return 3
+    def main_next_row_columns(self): return [0, 1]
+    def max_constraint_degree(self): return 2
+
+    def eval_folded_constraints(self, e, loc, nxt, pis, is_first, is_last, is_trans, alpha):
+        l, r, nl, nr = loc[0], loc[1], nxt[0], nxt[1]
+        cs = [e.mul(is_first, e.sub(l, e.base(pis[0]))), e.mul(is_first, e.sub(r, e.base(pis[1]))),
+              e.mul(is_trans, e.sub(r, nl)), e.mul(is_trans, e.sub(e.add(l, r), nr)), e.mul(is_last, e.sub(r, e.base(pis[2])))]
+        acc = [0, 0, 0, 0]
+        for c in cs:
+            acc = e.add(e.mul(acc, alpha), c)
+        return acc

@@ -86,6 +86,41 @@ def test_prove_matches_cpu_replay(setup, log_n, num_queries, pow_bits):
     raw = proof.to_postcard()
     assert raw == R.to_wire_proof(exp).to_postcard()
     V.verify(V.Fld(f.id), R.verifier_config(o16, o24, num_queries=num_queries, query_pow_bits=pow_bits), V.poseidon2_air(oair), proof_from_postcard(raw))
+    # and the product's verifier with the batch hashing and the transcript on the GPU (plonky3_b200.verifier)
+    from plonky3_b200.uni_stark import verify
+    from plonky3_b200.verifier import VerificationError
+    verify(config, air, proof)
+    bad = bytearray(raw); bad[len(raw) // 2] ^= 4
+    with pytest.raises(VerificationError):
+        verify(config, air, bytes(bad))
+
+
+def test_gpu_verifier_on_the_reference_fixture(setup):
+    """The reference's committed proof (uni-stark/tests/fixtures/uni_stark_two_adic_v1.postcard, bytes in the golden JSON) is accepted
+    by plonky3_b200.verifier with Poseidon2 leaf hashing, node compression and the duplex challenger on the GPU; a wrong public
+    value and corrupted bytes are rejected."""
+    import json
+    import pathlib
+    import fixture_replay as FR
+    import stark_verify as V
+    from plonky3_b200.field import BabyBear
+    from plonky3_b200.uni_stark import verify
+    from plonky3_b200.verifier import VerificationError
+    gpu = setup[0]
+    gold = json.loads((pathlib.Path(__file__).resolve().parent / "golden" / "uni_stark_two_adic_v1.json").read_text())
+    raw = bytes.fromhex(gold["postcard_hex"])
+    rc_i, rc_t, rc_p = FR.fixture_constants()
+    pm = Poseidon2.new(BabyBear, 16, rc_i, rc_t, rc_p, monty=True)
+    mmcs = MerkleTreeMmcs.poseidon2(pm, None, 0, gpu)
+    pcs = TwoAdicFriPcs(Radix2DitParallel(BabyBear, gpu), mmcs, FriParameters(2, 2, 1, 2, 1, 1, mmcs))       # fib_air.rs:134-155
+    config = StarkConfig(pcs, pm, 8)                                                                         # DuplexChallenger<Val, Perm, 16, 8>
+    verify(config, V.FibonacciAir(), raw, [0, 1, 21])
+    with pytest.raises(VerificationError):
+        verify(config, V.FibonacciAir(), raw, [0, 1, 22])
+    for pos in range(2, len(raw) - 1, 97):
+        bad = bytearray(raw); bad[pos] ^= 1
+        with pytest.raises(VerificationError):
+            verify(config, V.FibonacciAir(), bytes(bad), [0, 1, 21])
 
 
 def test_challenger_matches_oracle(setup):

@@ -422,6 +422,49 @@ def test_verifier_accepts_the_reference_proof_fixture():
     assert rejected >= 38
 
 
+def test_product_verifier_on_the_reference_fixture():
+    """plonky3_b200.verifier.verify — the product's verifier, whose hashing and transcript go through the configuration's MMCS and
+    challenger (the GPU ones in tests/test_gpu_prove.py, oracle-backed stand-ins here) — accepts the reference's committed proof,
+    rejects a wrong statement and every corruption."""
+    from plonky3_b200.field import BabyBear
+    from plonky3_b200.verifier import VerificationError, verify
+    V, _, cfg = _fixture_verifier_setup()
+    gold = json.loads((GOLD / "uni_stark_two_adic_v1.json").read_text())
+    raw = bytes.fromhex(gold["postcard_hex"])
+    config = V.product_config(BabyBear, cfg)
+    verify(config, V.FibonacciAir(), raw, [0, 1, 21])
+    with pytest.raises(VerificationError):
+        verify(config, V.FibonacciAir(), raw, [0, 1, 22])
+    for pos in list(range(2, len(raw) - 1, 29)) + [len(raw) - 6]:
+        bad = bytearray(raw); bad[pos] ^= 1
+        with pytest.raises(VerificationError):
+            verify(config, V.FibonacciAir(), bytes(bad), [0, 1, 21])
+
+
+def test_verify_multi_batch_mixed_heights():
+    """verify_multi_batch_with on a tree over matrices of three heights (injection, merkle_tree.rs:348-): openings built from the
+    oracle's tree verify; a wrong row, a wrong digest, a missing or an extra digest do not."""
+    import stark_verify as V
+    from plonky3_b200.merkle_tree import MerkleTreeError, prune_paths
+    hs = O.poseidon2_hasher(O.default_perm(KB, 24), O.default_perm(KB, 16))
+    mats = [O.random_matrix(KB, 64, 5, seed=1), O.random_matrix(KB, 16, 3, seed=2), O.random_matrix(KB, 64, 2, seed=3), O.random_matrix(KB, 8, 9, seed=4)]
+    layers = O.merkle_tree(hs, mats)
+    mm = V.OracleMmcs(hs)
+    dims = [(m.shape[1], m.shape[0]) for m in mats]
+    for cap_height in (0, 2, 3):
+        cap = O.merkle_cap(layers, cap_height)
+        idx = [5, 40, 41, 5, 63]
+        ov = [[m[i >> (6 - (m.shape[0].bit_length() - 1))] for m in mats] for i in idx]
+        paths = np.array([[layers[l][(i >> l) ^ 1] for l in range(6 - cap_height)] for i in idx], dtype=np.uint32).reshape(len(idx), 6 - cap_height, 8)
+        pr = prune_paths(idx, paths)
+        mm.verify_multi_batch(cap, dims, idx, ov, pr)
+        bad_rows = [[r.copy() for r in q] for q in ov]; bad_rows[1][3][0] ^= 1
+        for args in ((cap, dims, idx, bad_rows, pr), (cap, dims, idx, ov, pr[:-1]), (cap, dims, idx, ov, np.concatenate([pr, pr[:1]])),
+                     (cap, dims, idx, ov, np.concatenate([pr[:1] ^ 1, pr[1:]])), (cap, dims, [6] + idx[1:], ov, pr)):
+            with pytest.raises(MerkleTreeError):
+                mm.verify_multi_batch(*args)
+
+
 def test_prove_replay_proof_verifies():
     """The Poseidon2-AIR proof of the CPU replay prover (the one the GPU prover is compared against bit for bit), serialised to the
     reference's wire form and read back, is accepted by the restated verifier; a tampered one is not."""
@@ -441,6 +484,15 @@ def test_prove_replay_proof_verifies():
         bad = bytearray(raw); bad[pos] ^= 4
         with pytest.raises((V.VerifyError, ValueError)):
             V.verify(f, cfg, V.poseidon2_air(air), proof_from_postcard(bytes(bad)))
+    # the product verifier with its own AIR class (constraint folder on the host, no device needed for verification)
+    from plonky3_b200.field import KoalaBear
+    from plonky3_b200.uni_stark import RoundConstants, VectorizedPoseidon2Air
+    from plonky3_b200.verifier import VerificationError, verify
+    pair = VectorizedPoseidon2Air(KoalaBear, RoundConstants(np.array(air.beg).reshape(4, 16), np.array(air.part)[: air.rounds_p], np.array(air.end).reshape(4, 16)), None)
+    verify(V.product_config(KoalaBear, cfg), pair, raw)
+    bad = bytearray(raw); bad[len(raw) // 2] ^= 4
+    with pytest.raises(VerificationError):
+        verify(V.product_config(KoalaBear, cfg), pair, bytes(bad))
 
 
 # ---------------------------------------------------------------- Keccak: second, independent formulation
