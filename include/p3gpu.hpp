@@ -6,10 +6,15 @@
 //   p3gpu::Radix2DitParallel  ~ TwoAdicSubgroupDft          dft/src/traits.rs:28-291, radix_2_dit_parallel.rs:144-246
 //   p3gpu::MerkleTreeMmcs     ~ Mmcs::commit                merkle-tree/src/mmcs/batch.rs:42-64
 //   p3gpu::TwoAdicFriFolding  ~ FriFoldingStrategy          fri/src/two_adic_pcs.rs:134-213
+//   p3gpu::TwoAdicFriPcs      ~ Pcs::commit (host trace in, LDE + tree resident on the device)   fri/src/two_adic_pcs.rs:300-324
+//   p3gpu::MerkleTreeMmcs::open_multi_batch / prune_paths ~ Mmcs::open_multi_batch     merkle-tree/src/mmcs/mod.rs:276-428, pruning.rs
 #pragma once
+#include <algorithm>
 #include <cstdint>
+#include <map>
 #include <stdexcept>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "p3gpu.h"
@@ -30,6 +35,30 @@ class Context {
     p3gpu_ctx *raw() const { return ctx_; }
   private:
     p3gpu_ctx *ctx_ = nullptr;
+};
+
+// Device memory owned by the host object that holds it (p3gpu_malloc / p3gpu_free)
+class DeviceBuffer {
+  public:
+    DeviceBuffer() = default;
+    DeviceBuffer(Context &c, size_t words) : c_(&c), words_(words) { void *p = nullptr; check(p3gpu_malloc(c.raw(), std::max<size_t>(words, 1) * 4, &p)); ptr_ = (uint32_t *)p; }
+    ~DeviceBuffer() { if (ptr_) p3gpu_free(c_->raw(), ptr_); }
+    DeviceBuffer(DeviceBuffer &&o) noexcept : c_(o.c_), ptr_(o.ptr_), words_(o.words_) { o.ptr_ = nullptr; }
+    DeviceBuffer &operator=(DeviceBuffer &&o) noexcept { std::swap(c_, o.c_); std::swap(ptr_, o.ptr_); std::swap(words_, o.words_); return *this; }
+    DeviceBuffer(const DeviceBuffer &) = delete;
+    DeviceBuffer &operator=(const DeviceBuffer &) = delete;
+    uint32_t *data() const { return ptr_; }
+    size_t words() const { return words_; }
+    std::vector<uint32_t> to_host(size_t offset_words, size_t n_words) const {
+        if (offset_words + n_words > words_) throw Error("device read out of bounds");
+        std::vector<uint32_t> out(n_words);
+        if (n_words) check(p3gpu_memcpy_d2h(c_->raw(), out.data(), ptr_ + offset_words, n_words * 4));
+        return out;
+    }
+  private:
+    Context *c_ = nullptr;
+    uint32_t *ptr_ = nullptr;
+    size_t words_ = 0;
 };
 
 struct RowMajorMatrix {                 // matrix/src/dense.rs:23-36
@@ -95,6 +124,88 @@ class MerkleTreeMmcs {
     }
   private:
     Context &c_; int field_, hash_; size_t cap_height_;
+};
+
+// What Pcs::commit keeps for the rest of the proof: the committed LDE (bit-reversed rows) and every digest layer, on the device.
+struct DeviceProverData {
+    DeviceBuffer lde, layers;
+    std::vector<size_t> layer_lens;     // digests per layer, layer 0 = leaves
+    size_t height = 0, width = 0;       // of the LDE
+};
+
+// A multi-opening in the reference's wire shape (fri/src/proof.rs:68-75): opened_values[query] = the row, one pruned proof.
+struct MultiOpening {
+    std::vector<std::vector<uint32_t>> opened_values;
+    std::vector<uint32_t> pruned_digests;   // k * 8 words, wire order of merkle-tree/src/pruning.rs:187-232
+};
+
+// prune_paths for the binary schedule: `paths` = n * levels * 8 words (sibling digests bottom-up per query).  The sorted distinct
+// leaves fold up level by level; a node whose sibling is not on the frontier takes it from the smallest queried leaf below it.
+inline std::vector<uint32_t> prune_paths(const std::vector<uint32_t> &indices, const std::vector<uint32_t> &paths, size_t levels) {
+    if (paths.size() != indices.size() * levels * 8) throw Error("paths do not match indices x levels");
+    std::map<uint32_t, size_t> first;
+    for (size_t q = 0; q < indices.size(); q++) first.emplace(indices[q], q);
+    std::vector<std::pair<uint64_t, size_t>> nodes(first.begin(), first.end()), parents;
+    std::vector<uint32_t> out;
+    for (size_t level = 0; level < levels; level++) {
+        parents.clear();
+        for (size_t k = 0; k < nodes.size();) {
+            const uint64_t idx = nodes[k].first;
+            const size_t lead = nodes[k].second;
+            if (k + 1 < nodes.size() && nodes[k + 1].first == (idx ^ 1)) k += 2;
+            else {
+                const uint32_t *d = &paths[(lead * levels + level) * 8];
+                out.insert(out.end(), d, d + 8);
+                k += 1;
+            }
+            parents.emplace_back(idx >> 1, lead);
+        }
+        nodes.swap(parents);
+    }
+    return out;
+}
+
+class TwoAdicFriPcs {
+  public:
+    TwoAdicFriPcs(Context &c, int field, int hash, unsigned log_blowup, size_t cap_height)
+        : c_(c), field_(field), hash_(hash), log_blowup_(log_blowup), cap_height_(cap_height) {}
+    // Pcs::commit for one trace over the subgroup H: (cap, prover data).  The trace crosses PCIe once; only the cap comes back.
+    std::pair<std::vector<uint32_t>, DeviceProverData> commit(const RowMajorMatrix &evals) const {
+        const size_t h = evals.height(), w = evals.width, H = h << log_blowup_;
+        if (h == 0 || (h & (h - 1))) throw Error("trace height must be a power of two");
+        DeviceProverData pd;
+        pd.height = H; pd.width = w;
+        pd.lde = DeviceBuffer(c_, H * w);
+        pd.layers = DeviceBuffer(c_, p3gpu_merkle_total_digests(H) * 8);
+        size_t lens[65], n = 0, cap_len = 0;
+        std::vector<uint32_t> cap(((size_t)1 << cap_height_) * 8);
+        check(p3gpu_pcs_commit(c_.raw(), field_, hash_, evals.values.data(), h, w, log_blowup_, (unsigned)cap_height_, pd.lde.data(),
+                               pd.layers.data(), lens, &n, cap.data(), &cap_len));
+        pd.layer_lens.assign(lens, lens + n);
+        cap.resize(cap_len * 8);
+        return {std::move(cap), std::move(pd)};
+    }
+    // Mmcs::open_multi_batch on the committed data: rows gathered and paths walked on the device, pruned on the host
+    MultiOpening open_multi_batch(const std::vector<uint32_t> &indices, const DeviceProverData &pd) const {
+        const size_t n = indices.size(), nl = pd.layer_lens.size();
+        for (uint32_t i : indices) if (i >= pd.height) throw Error("index out of bounds for height " + std::to_string(pd.height));
+        const size_t eff = std::min(cap_height_, nl ? nl - 1 : 0), path_len = nl - 1 - eff;
+        DeviceBuffer rows(c_, n * pd.width), paths(c_, n * path_len * 8);
+        MultiOpening out;
+        if (n == 0) return out;
+        check(p3gpu_gather_rows_dev(c_.raw(), pd.lde.data(), pd.height, pd.width, indices.data(), n, 0, rows.data()));
+        const std::vector<uint32_t> flat = rows.to_host(0, n * pd.width);
+        for (size_t q = 0; q < n; q++) out.opened_values.emplace_back(flat.begin() + q * pd.width, flat.begin() + (q + 1) * pd.width);
+        std::vector<uint32_t> full;
+        if (path_len) {
+            check(p3gpu_merkle_paths_dev(c_.raw(), pd.layers.data(), pd.layer_lens.data(), nl, path_len, indices.data(), n, 0, paths.data()));
+            full = paths.to_host(0, n * path_len * 8);
+        }
+        out.pruned_digests = prune_paths(indices, full, path_len);
+        return out;
+    }
+  private:
+    Context &c_; int field_, hash_; unsigned log_blowup_; size_t cap_height_;
 };
 
 class TwoAdicFriFolding {

@@ -94,6 +94,26 @@ def test_cpp_host_mirror_compiles_and_fails_loudly_without_gpu(tmp_path):
         assert r.returncode == 3 and "no CPU fallback" in r.stdout, r.stdout + r.stderr
 
 
+def test_cpp_prune_paths_matches_python(tmp_path):
+    """p3gpu::prune_paths (include/p3gpu.hpp, host-only) against plonky3_b200.merkle_tree.prune_paths, which the reference's
+    committed proof pins (tests/test_oracle.py)."""
+    import subprocess
+    from plonky3_b200.merkle_tree import prune_paths
+    exe = tmp_path / "prune_check"
+    lib_dir = ROOT / "plonky3_b200"
+    subprocess.run(["/usr/bin/g++", "-std=c++17", "-O1", "-I", str(ROOT / "include"), str(ROOT / "tests" / "cpp" / "prune_check.cpp"),
+                    "-o", str(exe), f"-L{lib_dir}", "-l:libp3gpu.so", f"-Wl,-rpath,{lib_dir}"], check=True)
+    rng = np.random.default_rng(5)
+    for levels, n in [(1, 1), (3, 2), (5, 7), (10, 100), (6, 150), (4, 0)]:
+        idx = [int(v) for v in rng.integers(0, 1 << levels, n)]
+        layers = [rng.integers(0, 1 << 32, ((1 << levels) >> l, 8), dtype=np.uint32) for l in range(levels)]
+        paths = np.array([[layers[l][(i >> l) ^ 1] for l in range(levels)] for i in idx], dtype=np.uint32).reshape(n, levels, 8)
+        text = f"{levels} {n}\n" + "".join(f"{i} " + " ".join(f"{w:x}" for w in paths[q].ravel()) + "\n" for q, i in enumerate(idx))
+        r = subprocess.run([str(exe)], input=text, capture_output=True, text=True, check=True)
+        got = np.array([int(w, 16) for w in r.stdout.split()], dtype=np.uint32).reshape(-1, 8)
+        assert np.array_equal(got, prune_paths(idx, paths)), (levels, n)
+
+
 def test_device_arithmetic_source_on_the_host(tmp_path):
     """csrc/field.cuh (the arithmetic every kernel is built from) compiled as plain C++ and run on the host: Montgomery and Shoup
     multiplies, the lazy [0, 2p) butterfly contract for any 32-bit input, EF4 products and the two-adic generators, for both

@@ -632,3 +632,44 @@ def test_batch_stark_fixture_main_commitment_on_gpu(gpu):
         cap = batch_fixture_main_cap(lambda m, bits, s: dft.coset_lde_batch(to(m), bits, s).bit_reverse_rows(), lambda mats: mmcs.commit(mats)[0])
         assert np.asarray(cap).tolist() == gold["main_cap"]
     default_poseidon2(BabyBear, 16).upload(gpu)                        # restore the default constants for the other tests
+
+
+def test_cpp_host_mirror_pcs_commit_and_multi_opening(gpu, tmp_path):
+    """include/p3gpu.hpp on the GPU: TwoAdicFriPcs::commit (host trace in, cap out, LDE + tree resident) and open_multi_batch with
+    the pruned multiproof, from a C++ program (tests/cpp/pcs_commit_check.cpp), against the oracle; plus the small DFT/commit
+    program of the link test."""
+    import subprocess
+    from plonky3_b200.merkle_tree import prune_paths
+    root = pathlib.Path(__file__).resolve().parent.parent
+    lib_dir = root / "plonky3_b200"
+
+    def build(name):
+        exe = tmp_path / name
+        subprocess.run(["/usr/bin/g++", "-std=c++17", "-O1", "-I", str(root / "include"), str(root / "tests" / "cpp" / f"{name}.cpp"), "-o", str(exe),
+                        f"-L{lib_dir}", "-l:libp3gpu.so", f"-Wl,-rpath,{lib_dir}"], check=True)
+        return exe
+    r = subprocess.run([str(build("host_mirror_check"))], capture_output=True, text=True)
+    assert r.returncode == 0 and "gpu ok" in r.stdout, r.stdout + r.stderr
+    exe = build("pcs_commit_check")
+    hs = O.keccak_hasher()
+    for f, log_h, w, log_blowup, cap_height, idx in [(BabyBear, 6, 5, 1, 2, [5, 40, 41, 5, 127]), (KoalaBear, 10, 33, 2, 0, [0, 4095, 17, 18, 2048]),
+                                                     (KoalaBear, 3, 1, 1, 3, [1, 15])]:
+        r = subprocess.run([str(exe), str(f.id), str(_lib.HASH_KECCAK), str(log_h), str(w), str(log_blowup), str(cap_height), ",".join(map(str, idx))],
+                           capture_output=True, text=True)
+        assert r.returncode == 0, r.stdout + r.stderr
+        lines = [l.split() for l in r.stdout.strip().splitlines()]
+        words = lambda l: np.array([int(x, 16) for x in l[1:]], dtype=np.uint32)
+        s, vals = 12345, []
+        for _ in range((1 << log_h) * w):                         # the program's LCG
+            s = (s * 6364136223846793005 + 1442695040888963407) & ((1 << 64) - 1)
+            vals.append((s >> 33) % f.P)
+        m = np.array(vals, dtype=np.uint32).reshape(1 << log_h, w)
+        lde = O.coset_lde_batch(f.id, m, log_blowup, f.generator, bitrev_out=True)
+        layers = O.merkle_tree(hs, [lde])
+        eff = min(cap_height, len(layers) - 1)
+        assert lines[0][0] == "cap" and np.array_equal(words(lines[0]).reshape(-1, 8), O.merkle_cap(layers, eff))
+        rows = [words(l) for l in lines if l[0] == "row"]
+        assert len(rows) == len(idx) and all(np.array_equal(r_, lde[i]) for r_, i in zip(rows, idx))
+        paths = np.array([[layers[l][(i >> l) ^ 1] for l in range(len(layers) - 1 - eff)] for i in idx], dtype=np.uint32).reshape(len(idx), -1, 8)
+        pruned = words([l for l in lines if l[0] == "pruned"][0]).reshape(-1, 8)
+        assert np.array_equal(pruned, prune_paths(idx, paths))
