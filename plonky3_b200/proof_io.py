@@ -61,16 +61,22 @@ def proof_to_postcard(proof) -> bytes:
     out += _varint(len(proof.input_openings))
     for (rows, paths), idx in zip(proof.input_openings, proof.input_opening_indices):
         out += _varint(len(idx))
-        for q in range(len(idx)):
-            out += _varint(len(rows))
+        if len(idx):                                              # all queries have the same byte layout: assemble them as one (n, bytes) block
+            n = len(idx)
+            parts = [np.tile(np.frombuffer(_varint(len(rows)), dtype=np.uint8), (n, 1))]
             for m in rows:
-                out += _varint(int(np.asarray(m).shape[1])) + _words(np.asarray(m)[q])
+                m = np.ascontiguousarray(np.asarray(m, dtype=np.uint32).reshape(n, -1)).astype("<u4")
+                parts.append(np.tile(np.frombuffer(_varint(m.shape[1]), dtype=np.uint8), (n, 1)))
+                parts.append(m.view(np.uint8).reshape(n, -1))
+            out += np.hstack(parts).tobytes()
         out += _vec_of(prune_paths(idx, paths), 8)
     out += _varint(len(proof.commit_phase_openings))
     for (log_arity, siblings, paths), idx in zip(proof.commit_phase_openings, proof.commit_phase_indices):
         out += bytes([log_arity]) + _varint(len(idx))
-        for q in range(len(idx)):
-            out += _vec_of(np.asarray(siblings)[q], 4)
+        if len(idx):
+            sib = np.ascontiguousarray(np.asarray(siblings, dtype=np.uint32).reshape(len(idx), -1)).astype("<u4")      # (n, (arity - 1) * 4)
+            pre = np.tile(np.frombuffer(_varint(sib.shape[1] // 4), dtype=np.uint8), (len(idx), 1))
+            out += np.hstack([pre, sib.view(np.uint8).reshape(len(idx), -1)]).tobytes()
         out += _vec_of(prune_paths(idx, paths), 8)
     out += _vec_of(proof.final_poly, 4) + _words([proof.query_pow_witness]) + _varint(proof.degree_bits)
     return bytes(out)
