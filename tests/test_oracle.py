@@ -441,6 +441,25 @@ def test_product_verifier_on_the_reference_fixture():
             verify(config, V.FibonacciAir(), bytes(bad), [0, 1, 21])
 
 
+@pytest.mark.parametrize("f", [BB, KB])
+def test_fold_row_agrees_with_fold_matrix(f):
+    """fri/src/two_adic_pcs.rs tests `fold_matrix_matches_fold_row`: the verifier's Lagrange-form fold_row (plonky3_b200.verifier) on
+    every row equals the prover's butterfly-form fold_matrix (oracle), for every arity and several heights."""
+    from plonky3_b200.field import BabyBear, KoalaBear
+    from plonky3_b200.verifier import Ext, fold_row
+    e = Ext(BabyBear if f == BB else KoalaBear)
+    for log_arity in (1, 2, 3, 4):
+        for log_h in (0, 1, 3, 5):
+            n = 1 << (log_h + log_arity)
+            vec = O.random_matrix(f, n, 4, seed=7 * log_arity + log_h)
+            beta = O.random_matrix(f, 1, 4, seed=99)[0]
+            exp = O.fold_matrix(f, vec, log_arity, beta)
+            rows = vec.reshape(1 << log_h, 1 << log_arity, 4)
+            for i in range(1 << log_h):
+                got = fold_row(e, i, log_h, log_arity, e.ec(beta), [e.ec(v) for v in rows[i]])
+                assert [e.m(v) for v in got] == [int(v) for v in exp[i]], (log_arity, log_h, i)
+
+
 def test_verify_multi_batch_mixed_heights():
     """verify_multi_batch_with on a tree over matrices of three heights (injection, merkle_tree.rs:348-): openings built from the
     oracle's tree verify; a wrong row, a wrong digest, a missing or an extra digest do not."""
