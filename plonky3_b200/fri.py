@@ -255,6 +255,40 @@ class TwoAdicFriPcs:
         fri_inputs = [reduced[lh] for lh in sorted(reduced, reverse=True)]
         return all_opened, fri_inputs
 
+    # ---- Pcs::open / Pcs::verify (two_adic_pcs.rs:413-715) as whole operations
+    def open(self, data_with_points: list, challenger):
+        """Pcs::open: opened values of every matrix at every point + the FRI opening proof (fri/src/proof.rs FriProof, as the dict
+        proof_io / verifier use: multi-openings with pruned multiproofs).  `data_with_points` as in open_values_and_fri_inputs."""
+        from .merkle_tree import prune_paths
+        from .uni_stark import prove_fri
+        opened, fri_inputs = self.open_values_and_fri_inputs(data_with_points, challenger)
+        fri = prove_fri(self, fri_inputs, challenger, data_with_points)
+        nq = len(fri["indices"])
+        proof = {
+            "commit_phase_commits": fri["commits"], "commit_pow_witnesses": fri["pow_witnesses"], "final_poly": fri["final_poly"],
+            "query_pow_witness": fri["query_pow_witness"],
+            "input_openings": [{"opened_values": [[rows[m][q] for m in range(len(rows))] for q in range(nq)], "proof": prune_paths(idx, paths)}
+                               for (rows, paths), idx in zip(fri["input_openings"], fri["input_opening_indices"])],
+            "commit_phase_openings": [{"log_arity": la, "sibling_values": [sib[q] for q in range(nq)], "proof": prune_paths(idx, paths)}
+                                      for (la, sib, paths), idx in zip(fri["commit_phase_openings"], fri["commit_phase_indices"])],
+        }
+        return opened, proof
+
+    def verify(self, commitments_with_opening_points: list, proof: dict, challenger):
+        """Pcs::verify (two_adic_pcs.rs:684-715): `commitments_with_opening_points` = [(commitment, [((shift, log_size), [(z, values)])])]
+        with z (4,) and values (width, 4) Montgomery words, in commitment order.  Raises verifier.VerificationError."""
+        from .verifier import Ext, verify_fri
+        e = Ext(self.dft.field)
+        rounds = []
+        for commit, mats in commitments_with_opening_points:
+            rmats = []
+            for (_, log_size), pts in mats:
+                for _, ys in pts:
+                    challenger.observe_algebra_slice(np.asarray(ys, dtype=np.uint32))
+                rmats.append((log_size, [(e.ec(z), [e.ec(v) for v in np.asarray(ys, dtype=np.uint32).reshape(-1, 4)]) for z, ys in pts]))
+            rounds.append((commit, rmats))
+        verify_fri(e, self.fri, self.mmcs, proof, challenger, rounds)
+
     def get_evaluations_on_domain(self, prover_data, idx: int, domain):
         """two_adic_pcs.rs:376-403.  Fast path: the first |domain| rows of the committed bit-reversed LDE (domain shift =
         GENERATOR, |domain| <= LDE height).  Slow path (:390-403): un-bit-reverse, coset iDFT over GENERATOR*H' to recover the

@@ -159,3 +159,56 @@ def test_open_multi_batch_matches_open_batch(setup):
     _, htree = mmcs.commit([a, b])                                                      # host-resident prover data
     hrows, hpaths = mmcs.open_multi_batch(idx, htree)
     assert all(np.array_equal(x, y) for x, y in zip(rows, hrows)) and np.array_equal(paths, hpaths)
+
+
+@pytest.mark.parametrize("log_blowup,log_final_poly_len,max_log_arity,cap_height", [(1, 0, 1, 0), (1, 2, 2, 2), (2, 1, 3, 1), (1, 3, 4, 0)])
+def test_pcs_commit_open_verify_mixed_heights(setup, log_blowup, log_final_poly_len, max_log_arity, cap_height):
+    """fri/tests/pcs.rs (the macro suite: several rounds, matrices of different heights in one batch, one or two opening points,
+    blowup 1/2, arity 2..16, final polynomial 1..8 coefficients): Pcs::commit -> Pcs::open on the GPU, Pcs::verify by the product
+    verifier (hashing on the GPU); a tampered opened value, opened row, multiproof digest, sibling value and final polynomial are
+    rejected."""
+    from plonky3_b200.challenger import DuplexChallenger
+    from plonky3_b200.verifier import VerificationError
+    gpu, oair, o16, o24, p16, p24 = setup
+    mmcs = MerkleTreeMmcs.poseidon2(p16, p24, cap_height=cap_height, gpu=gpu)
+    pcs = TwoAdicFriPcs(Radix2DitParallel(f, gpu), mmcs, FriParameters(log_blowup, log_final_poly_len, max_log_arity, 9, 1, 3, mmcs))
+    g = torch.Generator(device="cuda"); g.manual_seed(11 * log_blowup + max_log_arity)
+    shapes = [[(5, 3), (8, 2)], [(8, 1), (7, 4), (5, 2)]]                  # per round: (log degree, width)
+
+    def transcript_head(ch, commits):
+        for c in commits:
+            ch.observe_cap(c)
+        return [ch.sample_algebra_element() for _ in range(2)]
+    commits, datas = [], []
+    for rnd in shapes:
+        evals = [((f.ONE, d), torch.randint(0, f.P, (1 << d, w), device="cuda", dtype=torch.int32, generator=g)) for d, w in rnd]
+        c, pd = pcs.commit(evals)
+        commits.append(c); datas.append(pd)
+    ch = DuplexChallenger(f, p24, 16, gpu)
+    zeta, zeta2 = transcript_head(ch, commits)
+    points = [[[zeta], [zeta, zeta2]], [[zeta2], [zeta], [zeta, zeta2]]]
+    opened, proof = pcs.open(list(zip(datas, points)), ch)
+
+    def claims(opened_values):
+        return [(c, [((f.ONE, d), [(z, ys) for z, ys in zip(pts, ov)]) for (d, _), pts, ov in zip(rnd, rpts, rov)])
+                for c, rnd, rpts, rov in zip(commits, shapes, points, opened_values)]
+
+    def check(opened_values, prf):
+        chv = DuplexChallenger(f, p24, 16, gpu)
+        z1, z2 = transcript_head(chv, commits)
+        assert np.array_equal(z1, zeta) and np.array_equal(z2, zeta2)
+        pcs.verify(claims(opened_values), prf, chv)
+    check(opened, proof)
+    import copy
+    bad = copy.deepcopy(opened); bad[1][1][0][2][1] ^= 1
+    with pytest.raises(VerificationError):
+        check(bad, proof)
+    for mutate in (lambda p: p["input_openings"][0]["opened_values"][3][1].__setitem__(0, int(p["input_openings"][0]["opened_values"][3][1][0]) ^ 1),
+                   lambda p: p["input_openings"][1]["proof"].__setitem__((0, 0), int(p["input_openings"][1]["proof"][0, 0]) ^ 1),
+                   lambda p: p["commit_phase_openings"][0]["sibling_values"][2].__setitem__((0, 0), int(p["commit_phase_openings"][0]["sibling_values"][2][0, 0]) ^ 1),
+                   lambda p: p["final_poly"].__setitem__((0, 0), int(p["final_poly"][0, 0]) ^ 1),
+                   lambda p: p["commit_phase_openings"].pop()):
+        prf = copy.deepcopy(proof)
+        mutate(prf)
+        with pytest.raises(VerificationError):
+            check(opened, prf)
