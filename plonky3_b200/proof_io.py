@@ -83,8 +83,8 @@ def proof_to_postcard(proof) -> bytes:
 
 
 class _Reader:
-    def __init__(self, data: bytes):
-        self.b, self.pos = data, 0
+    def __init__(self, data: bytes, prime=None):
+        self.b, self.pos, self.prime = data, 0, prime
 
     def varint(self) -> int:
         r = s = 0
@@ -97,6 +97,8 @@ class _Reader:
                 return r
 
     def byte(self) -> int:
+        if self.pos >= len(self.b):
+            raise ValueError("truncated proof")
         self.pos += 1
         return self.b[self.pos - 1]
 
@@ -105,6 +107,8 @@ class _Reader:
             raise ValueError("truncated proof")
         a = np.frombuffer(self.b, dtype="<u4", count=n, offset=self.pos).astype(np.uint32)
         self.pos += 4 * n
+        if self.prime is not None and n and int(a.max()) >= self.prime:
+            raise ValueError("Value is out of range")               # MontyField31::deserialize (monty-31/src/monty_31.rs:181-196)
         return a
 
     def vec_of(self, width: int) -> np.ndarray:
@@ -118,10 +122,11 @@ class _Reader:
         return self.vec_of(4) if tag else None
 
 
-def proof_from_postcard(data: bytes) -> dict:
+def proof_from_postcard(data: bytes, prime=None) -> dict:
     """The inverse: every field of the wire proof as arrays of Montgomery words (pruned multiproofs are left pruned — the
-    verifier restores them against its own query indices, merkle_tree.restore_paths)."""
-    r = _Reader(data)
+    verifier consumes them against its own query indices).  With `prime` given, words >= prime are rejected as the reference's
+    deserialiser rejects them (one field element has one encoding).  Raises ValueError on malformed input."""
+    r = _Reader(data, prime)
     p = {"trace_commit": r.vec_of(8), "quotient_commit": r.vec_of(8)}
     if r.byte() != 0:
         raise ValueError("ZK (random) commitments are not supported")

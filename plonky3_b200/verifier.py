@@ -226,7 +226,7 @@ def verify(config, air, proof, public_values=()):
         proof = proof.to_postcard()
     if isinstance(proof, (bytes, bytearray)):
         try:
-            proof = proof_from_postcard(bytes(proof))
+            proof = proof_from_postcard(bytes(proof), config.pcs.dft.field.P)
         except ValueError as ex:
             raise VerificationError(f"malformed proof: {ex}") from None
     pcs = config.pcs

@@ -439,6 +439,18 @@ def test_product_verifier_on_the_reference_fixture():
         bad = bytearray(raw); bad[pos] ^= 1
         with pytest.raises(VerificationError):
             verify(config, V.FibonacciAir(), bytes(bad), [0, 1, 21])
+    # one encoding per field element: the same final polynomial with its first coefficient written as w + p (>= p, fits in 32 bits
+    # for BabyBear) is refused, as MontyField31::deserialize refuses it; truncations never escape as another exception type
+    import struct
+    off = len(raw) - 1 - 4 - 64
+    w = struct.unpack_from("<I", raw, off)[0]
+    assert w + BabyBear.P < 1 << 32
+    alias = raw[:off] + struct.pack("<I", w + BabyBear.P) + raw[off + 4:]
+    with pytest.raises(VerificationError, match="out of range"):
+        verify(config, V.FibonacciAir(), alias, [0, 1, 21])
+    for cut in (1, 5, 70, 400, 1000, len(raw) - 1):
+        with pytest.raises(VerificationError):
+            verify(config, V.FibonacciAir(), raw[:cut], [0, 1, 21])
 
 
 @pytest.mark.parametrize("f", [BB, KB])
