@@ -389,6 +389,53 @@ def test_prove_replay_satisfies_the_verifier_identity():
     assert not R.verify_constraints_at_zeta(air, broken)
 
 
+class Xoroshiro128Plus:
+    """rand_xoshiro Xoroshiro128Plus::seed_from_u64 (SplitMix64 fills the two state words); next_u32 = upper half of next_u64;
+    field samples by rejection of the top 31 bits, the accepted value being the Montgomery word (monty-31/src/monty_31.rs:154-165)."""
+
+    def __init__(self, seed):
+        m64, x, s = (1 << 64) - 1, seed, []
+        for _ in range(2):
+            x = (x + 0x9E3779B97F4A7C15) & m64
+            z = x
+            z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & m64
+            z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & m64
+            s.append(z ^ (z >> 31))
+        self.s0, self.s1 = s
+
+    def u32(self):
+        m64 = (1 << 64) - 1
+        rotl = lambda v, k: ((v << k) | (v >> (64 - k))) & m64
+        r = (self.s0 + self.s1) & m64
+        s1 = self.s1 ^ self.s0
+        self.s0 = rotl(self.s0, 24) ^ s1 ^ ((s1 << 16) & m64)
+        self.s1 = rotl(s1, 37)
+        return r >> 32
+
+    def field(self, p, n):
+        out = []
+        while len(out) < n:
+            v = self.u32() >> 1
+            if v < p:
+                out.append(v)
+        return np.array(out, dtype=np.uint32)
+
+
+@pytest.mark.parametrize("f,name", [(KB, "koala_bear"), (BB, "baby_bear")])
+@pytest.mark.parametrize("width", [16, 24])
+def test_poseidon2_rng_constant_kats(f, name, width):
+    """The reference's second family of Poseidon2 KATs: constants drawn by Poseidon2::new_from_rng_128 (4 x width initial, 4 x width
+    terminal, R_P internal — the order oracle.perm_from_rng and the prove replay rely on) from Xoroshiro128Plus seed 1."""
+    kat = json.loads((GOLD / "poseidon2_rng_kat.json").read_text())[f"{name}_{width}"]
+    rp = {(BB, 16): 13, (BB, 24): 21, (KB, 16): 20, (KB, 24): 23}[(f, width)]
+    rng = Xoroshiro128Plus(1)
+    p = O.prime(f)
+    init = rng.field(p, 4 * width); term = rng.field(p, 4 * width); internal = rng.field(p, rp)
+    pm = O.make_perm(f, width, init, term, internal, monty=True)
+    out = O.poseidon2_permute(pm, O.to_monty_arr(f, np.array(kat["input"], dtype=np.uint32)))
+    assert [int(v) for v in O.from_monty_arr(f, out)] == kat["expected"]
+
+
 def _fixture_verifier_setup():
     import stark_verify as V
     rc_i, rc_t, rc_p = FR.fixture_constants()
