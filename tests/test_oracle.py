@@ -389,6 +389,51 @@ def test_prove_replay_satisfies_the_verifier_identity():
     assert not R.verify_constraints_at_zeta(air, broken)
 
 
+# ---------------------------------------------------------------- sponge / compression structure vs the reference's mock tests
+def _padding_free_sponge(permute, width, rate, out, items):
+    """PaddingFreeSponge::hash_iter (symmetric/src/sponge.rs): overwrite the rate, permute after every full or trailing partial
+    block, no padding, squeeze the first `out` words."""
+    state = [0] * width
+    items = list(items)
+    for i in range(0, len(items), rate):
+        block = items[i:i + rate]
+        state[:len(block)] = block
+        state = permute(state)
+    return state[:out]
+
+
+def _truncated_permutation(permute, n, chunk, width, inputs):
+    """TruncatedPermutation::compress (symmetric/src/compression.rs:40-65): inputs side by side in a zeroed state, permute, truncate."""
+    state = [0] * width
+    for k, part in enumerate(inputs):
+        state[k * chunk:(k + 1) * chunk] = part
+    return permute(state)[:chunk]
+
+
+def test_sponge_and_compression_structure_vs_reference_mock_tests():
+    """The reference pins the sponge and the compression function with a plain-sum mock permutation (symmetric/src/sponge.rs:708-776,
+    compression.rs:113-179).  The generic restatements above reproduce those literals; the C oracle's Poseidon2 leaf hash and node
+    compression (what the GPU is compared with) equal the same generic code driven by the oracle's permutation."""
+    mock = lambda st: [sum(st)] * len(st)
+    assert _padding_free_sponge(mock, 4, 2, 2, [1, 2, 3, 4, 5]) == [44, 44]
+    assert _padding_free_sponge(mock, 4, 2, 2, []) == [0, 0]
+    assert _padding_free_sponge(mock, 6, 3, 2, [10, 20, 30]) == [60, 60]
+    assert _truncated_permutation(mock, 2, 4, 8, [[1, 2, 3, 4], [5, 6, 7, 8]]) == [36] * 4
+    assert _truncated_permutation(mock, 2, 4, 8, [[0] * 4, [0] * 4]) == [0] * 4
+    assert _truncated_permutation(mock, 2, 3, 10, [[1, 2, 3], [4, 5, 6]]) == [21] * 3
+    for f in (BB, KB):
+        p16, p24 = O.default_perm(f, 16), O.default_perm(f, 24)
+        perm = lambda pm: (lambda st: [int(v) for v in O.poseidon2_permute(pm, np.array(st, dtype=np.uint32))])
+        for leaf_pm, width, rate in ((p16, 16, 8), (p24, 24, 16)):
+            hs = O.poseidon2_hasher(leaf_pm, p16)
+            for n in (0, 1, 7, 8, 9, 16, 17, 33, 100):
+                row = O.random_matrix(f, 1, max(n, 1), seed=n + width)[0][:n]
+                exp = _padding_free_sponge(perm(leaf_pm), width, rate, 8, [int(v) for v in row])
+                assert [int(v) for v in O.hash_row(hs, row)] == exp, (f, width, n)
+            l, r = O.random_matrix(f, 2, 8, seed=5)
+            assert [int(v) for v in O.compress(hs, l, r)] == _truncated_permutation(perm(p16), 2, 8, 16, [[int(v) for v in l], [int(v) for v in r]])
+
+
 class Xoroshiro128Plus:
     """rand_xoshiro Xoroshiro128Plus::seed_from_u64 (SplitMix64 fills the two state words); next_u32 = upper half of next_u64;
     field samples by rejection of the top 31 bits, the accepted value being the Montgomery word (monty-31/src/monty_31.rs:154-165)."""
