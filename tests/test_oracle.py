@@ -723,3 +723,131 @@ def test_batch_stark_fixture_main_commitment():
     cap = batch_fixture_main_cap(lambda m, bits, s: O.coset_lde_batch(0, m, bits, s, bitrev_out=True),
                                  lambda mats: O.merkle_cap(O.merkle_tree(hs, mats), 1))
     assert cap.tolist() == gold["main_cap"]
+
+
+# ---------------------------------------------------------------- the product's prove driver on the CPU (device calls answered by the oracle)
+def test_prove_driver_host_logic_with_mock_device(monkeypatch):
+    """plonky3_b200.uni_stark.prove — the host-side sequencing of commit, quotient, commit_quotient, open, the FRI commit phase
+    with its arity schedule, PoW, query openings and the wire serialiser — executed on the CPU with every device call answered by
+    the oracle (tests/mock_device.py): the resulting proof equals the replay prover's byte for byte and verifies."""
+    import torch
+    from types import SimpleNamespace
+    import mock_device as M
+    import p2_prove_replay as R
+    import stark_verify as V
+    from plonky3_b200.dft import Radix2DitParallel
+    from plonky3_b200.field import KoalaBear
+    from plonky3_b200.fri import FriParameters, TwoAdicFriPcs
+    from plonky3_b200.merkle_tree import MerkleTreeMmcs
+    from plonky3_b200.poseidon2 import Poseidon2
+    from plonky3_b200.uni_stark import RoundConstants, VectorizedPoseidon2Air, prove
+    from plonky3_b200.verifier import verify
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)      # the driver's span timers synchronise the device
+    rng = O.SmallRng(1)
+    oair = O.air_from_rng(KB, rng)
+    o16 = O.perm_from_rng(KB, 16, rng); o24 = O.perm_from_rng(KB, 24, rng)
+    mk = lambda pm: Poseidon2.new(KoalaBear, pm.width, np.array(pm.rc_init)[: 4 * pm.width].reshape(4, pm.width),
+                                  np.array(pm.rc_term)[: 4 * pm.width].reshape(4, pm.width), np.array(pm.rc_int)[: pm.rounds_p], monty=True)
+    p16, p24 = mk(o16), mk(o24)
+    for log_n, nq, pow_bits in [(3, 4, 3), (5, 9, 5)]:
+        gpu = M.MockGpu()
+        mmcs = MerkleTreeMmcs.poseidon2(p16, p24, cap_height=3, gpu=gpu)
+        pcs = TwoAdicFriPcs(Radix2DitParallel(KoalaBear, gpu), mmcs, FriParameters(1, 0, 3, nq, 0, pow_bits, mmcs))
+        config = SimpleNamespace(pcs=pcs, initialise_challenger=lambda: M.MockChallenger(o24))
+        air = VectorizedPoseidon2Air(KoalaBear, RoundConstants(np.array(oair.beg).reshape(4, 16), np.array(oair.part)[: oair.rounds_p],
+                                                               np.array(oair.end).reshape(4, 16)), gpu)
+        inputs = O.SmallRng(1).field(KB, (8 << log_n) * 16).reshape(-1, 16)
+        trace = air.generate_trace_rows(torch.from_numpy(inputs.view(np.int32)))
+        proof = prove(config, air, trace)
+        exp = R.prove(oair, o16, o24, inputs, num_queries=nq, query_pow_bits=pow_bits)
+        raw = proof.to_postcard()
+        assert raw == R.to_wire_proof(exp).to_postcard()
+        assert {"coset_lde_batch", "merkle_commit", "p2air_quotient", "columnwise_dot", "rowwise_dot", "open_reduce", "fri_fold"} <= set(gpu.calls)
+        verify(V.product_config(KoalaBear, R.verifier_config(o16, o24, num_queries=nq, query_pow_bits=pow_bits)), air, raw)
+
+
+@pytest.mark.parametrize("log_blowup,log_final_poly_len,max_log_arity,cap_height", [(1, 0, 1, 0), (2, 1, 3, 1), (1, 3, 4, 2)])
+def test_pcs_round_trip_host_logic_with_mock_device(monkeypatch, log_blowup, log_final_poly_len, max_log_arity, cap_height):
+    """fri/tests/pcs.rs on the CPU: Pcs::commit -> open -> verify over two rounds with matrices of three heights in one batch and one
+    or two opening points, the product's host code throughout (device calls answered by the oracle); tampering is rejected.  The
+    GPU suite runs the same scenario with the real kernels (tests/test_gpu_prove.py)."""
+    import copy
+    import torch
+    import mock_device as M
+    import stark_verify as V
+    from plonky3_b200.dft import Radix2DitParallel
+    from plonky3_b200.field import KoalaBear
+    from plonky3_b200.fri import FriParameters, TwoAdicFriPcs
+    from plonky3_b200.merkle_tree import MerkleTreeMmcs
+    from plonky3_b200.poseidon2 import default_poseidon2
+    from plonky3_b200.verifier import VerificationError
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
+    f = KoalaBear
+    gpu = M.MockGpu()
+    p16, p24 = default_poseidon2(f, 16), default_poseidon2(f, 24)
+    o16, o24 = O.default_perm(KB, 16), O.default_perm(KB, 24)
+    mmcs = MerkleTreeMmcs.poseidon2(p16, p24, cap_height=cap_height, gpu=gpu)
+    pcs = TwoAdicFriPcs(Radix2DitParallel(f, gpu), mmcs, FriParameters(log_blowup, log_final_poly_len, max_log_arity, 6, 1, 2, mmcs))
+    vm = V.OracleMmcs(O.poseidon2_hasher(o24, o16))
+    pcs_v = TwoAdicFriPcs(Radix2DitParallel(f, gpu), vm, FriParameters(log_blowup, log_final_poly_len, max_log_arity, 6, 1, 2, vm))
+    shapes = [[(5, 3), (8, 2)], [(8, 1), (7, 4), (5, 2)]]
+    commits, datas = [], []
+    for r, rnd in enumerate(shapes):
+        evals = [((f.ONE, d), torch.from_numpy(O.random_matrix(KB, 1 << d, w, seed=10 * r + d + w).view(np.int32))) for d, w in rnd]
+        c, pd = pcs.commit(evals)
+        commits.append(c); datas.append(pd)
+
+    def head(ch):
+        for c in commits:
+            ch.observe_cap(c)
+        return ch.sample_algebra_element(), ch.sample_algebra_element()
+    ch = M.MockChallenger(o24)
+    zeta, zeta2 = head(ch)
+    points = [[[zeta], [zeta, zeta2]], [[zeta2], [zeta], [zeta, zeta2]]]
+    opened, proof = pcs.open(list(zip(datas, points)), ch)
+
+    def check(opened_values, prf):
+        chv = M.MockChallenger(o24)
+        head(chv)
+        claims = [(c, [((f.ONE, d), list(zip(pts, ov))) for (d, _), pts, ov in zip(rnd, rpts, rov)])
+                  for c, rnd, rpts, rov in zip(commits, shapes, points, opened_values)]
+        pcs_v.verify(claims, prf, chv)
+    check(opened, proof)
+    bad = copy.deepcopy(opened); bad[1][1][0][2][1] ^= 1
+    with pytest.raises(VerificationError):
+        check(bad, proof)
+    for mutate in (lambda p: p["input_openings"][0]["opened_values"][3][1].__setitem__(0, int(p["input_openings"][0]["opened_values"][3][1][0]) ^ 1),
+                   lambda p: p["input_openings"][1]["proof"].__setitem__((0, 0), int(p["input_openings"][1]["proof"][0, 0]) ^ 1),
+                   lambda p: p["commit_phase_openings"][0]["sibling_values"][2].__setitem__((0, 0), int(p["commit_phase_openings"][0]["sibling_values"][2][0, 0]) ^ 1),
+                   lambda p: p["final_poly"].__setitem__((0, 0), int(p["final_poly"][0, 0]) ^ 1),
+                   lambda p: p["commit_phase_openings"].pop()):
+        prf = copy.deepcopy(proof)
+        mutate(prf)
+        with pytest.raises(VerificationError):
+            check(opened, prf)
+
+
+def test_get_evaluations_on_domain_host_logic_with_mock_device():
+    """TwoAdicFriPcs::get_evaluations_on_domain (two_adic_pcs.rs:376-403) through the product's host code on the mock device: the fast
+    path (prefix of the committed LDE) and the slow path (coset iDFT, truncate, zero-pad, coset DFT onto a foreign coset) against a
+    direct oracle LDE of the same polynomials onto that coset."""
+    import torch
+    import mock_device as M
+    from plonky3_b200.dft import Radix2DitParallel
+    from plonky3_b200.field import KoalaBear as f
+    from plonky3_b200.fri import FriParameters, TwoAdicFriPcs
+    from plonky3_b200.merkle_tree import MerkleTreeMmcs
+    from plonky3_b200.poseidon2 import default_poseidon2
+    gpu = M.MockGpu()
+    mmcs = MerkleTreeMmcs.poseidon2(default_poseidon2(f, 16), default_poseidon2(f, 24), cap_height=0, gpu=gpu)
+    pcs = TwoAdicFriPcs(Radix2DitParallel(f, gpu), mmcs, FriParameters(1, 0, 1, 2, 0, 0, mmcs))
+    evals = O.random_matrix(KB, 1 << 5, 3, seed=4)
+    _, pd = pcs.commit([((f.ONE, 5), torch.from_numpy(evals.view(np.int32)))])
+    fast = pcs.get_evaluations_on_domain(pd, 0, (f.generator, 6)).bit_reverse_rows()
+    assert np.array_equal(fast.numpy().view(np.uint32), O.coset_lde_batch(KB, evals, 1, f.generator, bitrev_out=True))
+    for shift, log_size in [(f.mul(f.generator, f.two_adic_generator(7)), 6), (f.to_monty(5), 7), (f.to_monty(7), 5)]:
+        got = pcs.get_evaluations_on_domain(pd, 0, (shift, log_size)).to_row_major_matrix()
+        coeffs = O.idft_batch(KB, evals)
+        padded = np.zeros((1 << log_size, 3), dtype=np.uint32)
+        padded[: min(32, 1 << log_size)] = coeffs[: min(32, 1 << log_size)]
+        assert np.array_equal(np.asarray(got.numpy() if hasattr(got, "numpy") else got).view(np.uint32), O.coset_dft_batch(KB, padded, shift)), (shift, log_size)
