@@ -15,6 +15,8 @@ Layout = serde declaration order, postcard rules:
   PrunedMerklePaths{ sibling_hashes: Vec<[F; 8]> }                                                   merkle-tree/src/pruning.rs:83-89
   MerkleCap = Vec<[F; 8]>;  Vec = varint length + items;  Option = tag byte;  usize = varint;  u8 = one byte;  arrays carry no length;
   F = the 4 little-endian bytes of the Montgomery word (monty-31/src/monty_31.rs:167-179);  EF = 4 F.
+Digests are [F; 8] (the Poseidon2 MMCS of the example configurations); a Keccak MMCS commits to [u64; 4] digests, which postcard
+writes as varints — that configuration's proofs are not covered by this module.
 Pinned byte for byte against the reference's committed proof fixture (tests/golden/uni_stark_two_adic_v1.json `postcard_hex`)."""
 from __future__ import annotations
 
